@@ -1,0 +1,45 @@
+// Library-level entry points of the C ABI: version, thread-local error message, device info.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mc {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;  // B200
+    }
+    return cached;
+}
+
+}  // namespace mc
+
+extern "C" int mc_version(void) { return 100; }
+
+extern "C" const char* mc_last_error(void) { return mc::g_last_error; }
+
+extern "C" int mc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    MC_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return MC_OK;
+}

@@ -1,0 +1,502 @@
+// tcgen05 / TMEM / TMA batched GEMM engine with fused epilogue (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every tensor-core GEMM of the Mixer-CLIP step
+// (call sites k1, k4-k11, k16 of SURVEY.md 2.4; reference: nn.Linear lin1..lin4 + QuickGELU +
+// residual, training/clip/model.py:206-222; conv1 as im2col GEMM :258,272; projections :288,424;
+// and the dgrad / wgrad GEMMs autograd derives from them, training/training.py:170).
+//
+//   warp 0   : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1   : MMA issuer     (one thread, tcgen05.mma kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> global)
+//
+// Operand layouts are described, not materialised: a K-major operand is one TMA box of
+// [rows x 64] bf16 per stage; an MN-major operand (the "transposed" view: token-mixing reads the
+// [P x D] activation in place, wgrad reads activations as [K=tokens x M]) is ceil(rows/64) boxes of
+// [64 k-rows x 64] and the UMMA descriptor carries the MN-major canonical layout
+// (LBO = 8192 B between 64-wide groups, SBO = 1024 B between 8-row k groups).
+// Out-of-bounds parts of a box are zero-filled by TMA, so ragged M/N/K (50, 77, 197, 200, 308 ...)
+// need no padding copies of the activations; only rows whose byte pitch is not a multiple of 16 B
+// (token-mix weights) are re-packed by mc_cast_pad.
+#include "common.cuh"
+
+namespace mc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements per k-block = 128 B = one swizzle row
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr uint32_t kABytes = BM * BK * 2;  // 16384
+constexpr uint32_t kGroupBytes = 64 * BK * 2;  // one [64 x 64] bf16 box = 8192
+
+struct GemmTcArgs {
+    int M, N, K;
+    int out_batch, kb_per_batch, kb_total, k_spans_batch;
+    int a_mn, b_mn, a_batched, b_batched;
+    int BN, stages, stage_bytes, b_tx_bytes;
+    int tiles_m, tiles_n, split_k, num_tiles;
+    // epilogue
+    void* C;
+    int c_bf16;
+    long long ldc, c_bs;
+    int accumulate, atomic, row_remap, vec_ok;
+    const float* bias;
+    int bias_mode;
+    __nv_bfloat16* zout;
+    long long ldz, z_bs;
+    const __nv_bfloat16* zin;
+    long long ldzin, zin_bs;
+    int act;
+    const float* R;
+    long long ldr, r_bs;
+};
+
+struct TileCoord {
+    int tm, tn, b, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmTcArgs& g, int t) {
+    TileCoord c;
+    c.tm = t % g.tiles_m;
+    t /= g.tiles_m;
+    c.tn = t % g.tiles_n;
+    t /= g.tiles_n;
+    c.b = t % g.out_batch;
+    const int ks = t / g.out_batch;
+    c.kb_begin = int((long long)ks * g.kb_total / g.split_k);
+    c.kb_end = int((long long)(ks + 1) * g.kb_total / g.split_k);
+    return c;
+}
+
+// ---- epilogue on 8 consecutive columns held in registers ----------------------------------------
+__device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], float bias_m, long long crow, int b,
+                                          int n, int ncols, bool vec) {
+    // bias
+    if (g.bias_mode == MC_BIAS_N) {
+        if (vec) {
+            const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) x[j] += g.bias[n + j];
+        }
+    } else if (g.bias_mode == MC_BIAS_M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += bias_m;
+    }
+    // pre-activation store
+    if (g.zout != nullptr) {
+        __nv_bfloat16* zp = g.zout + (long long)b * g.z_bs + crow * g.ldz + n;
+        if (vec) {
+            uint4 pk;
+            pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
+            pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(zp) = pk;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) zp[j] = __float2bfloat16_rn(x[j]);
+        }
+    }
+    // activation
+    if (g.act == MC_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = quick_gelu_fast(x[j]);
+    } else if (g.act == MC_ACT_GELU_BWD) {
+        const __nv_bfloat16* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
+        if (vec) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(zp);
+            x[0] *= quick_gelu_grad_fast(bf16_lo(pk.x)); x[1] *= quick_gelu_grad_fast(bf16_hi(pk.x));
+            x[2] *= quick_gelu_grad_fast(bf16_lo(pk.y)); x[3] *= quick_gelu_grad_fast(bf16_hi(pk.y));
+            x[4] *= quick_gelu_grad_fast(bf16_lo(pk.z)); x[5] *= quick_gelu_grad_fast(bf16_hi(pk.z));
+            x[6] *= quick_gelu_grad_fast(bf16_lo(pk.w)); x[7] *= quick_gelu_grad_fast(bf16_hi(pk.w));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) x[j] *= quick_gelu_grad_fast(__bfloat162float(zp[j]));
+        }
+    }
+    // residual
+    if (g.R != nullptr) {
+        const float* rp = g.R + (long long)b * g.r_bs + crow * g.ldr + n;
+        if (vec) {
+            const float4 r0 = *reinterpret_cast<const float4*>(rp);
+            const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+            x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+            x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) x[j] += rp[j];
+        }
+    }
+    // store
+    if (g.c_bf16) {
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        if (vec) {
+            uint4 pk;
+            pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
+            pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(cp) = pk;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) cp[j] = __float2bfloat16_rn(x[j]);
+        }
+    } else {
+        float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        if (g.atomic) {
+            if (vec) {
+                atomicAdd(reinterpret_cast<float4*>(cp), make_float4(x[0], x[1], x[2], x[3]));
+                atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(x[4], x[5], x[6], x[7]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < ncols) atomicAdd(cp + j, x[j]);
+            }
+        } else if (vec) {
+            float4 o0 = make_float4(x[0], x[1], x[2], x[3]), o1 = make_float4(x[4], x[5], x[6], x[7]);
+            if (g.accumulate) {
+                const float4 c0 = *reinterpret_cast<const float4*>(cp);
+                const float4 c1 = *reinterpret_cast<const float4*>(cp + 4);
+                o0.x += c0.x; o0.y += c0.y; o0.z += c0.z; o0.w += c0.w;
+                o1.x += c1.x; o1.y += c1.y; o1.z += c1.z; o1.w += c1.w;
+            }
+            *reinterpret_cast<float4*>(cp) = o0;
+            *reinterpret_cast<float4*>(cp + 4) = o1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < ncols) cp[j] = g.accumulate ? cp[j] + x[j] : x[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs g) {
+    extern __shared__ uint8_t dyn_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull_bar[s]), 1);
+            mbar_init(smem_u32(&tempty_bar[s]), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(g, t);
+                const int m0 = tc.tm * BM, n0 = tc.tn * g.BN;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    int bb = tc.b, kk = kb * BK;
+                    if (g.k_spans_batch) {
+                        bb = kb / g.kb_per_batch;
+                        kk = (kb - bb * g.kb_per_batch) * BK;
+                    }
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    const uint32_t bar = smem_u32(&full_bar[stage]);
+                    const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
+                    const uint32_t b_dst = a_dst + kABytes;
+                    mbar_arrive_expect_tx(bar, kABytes + g.b_tx_bytes);
+                    const int ba = g.a_batched ? bb : 0, bbt = g.b_batched ? bb : 0;
+                    if (g.a_mn) {
+                        tma_load_3d(a_dst, &tmA, bar, m0, kk, ba);
+                        tma_load_3d(a_dst + kGroupBytes, &tmA, bar, m0 + 64, kk, ba);
+                    } else {
+                        tma_load_3d(a_dst, &tmA, bar, kk, m0, ba);
+                    }
+                    if (g.b_mn) {
+                        for (int j = 0; j * 64 < g.BN; ++j)
+                            tma_load_3d(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt);
+                    } else {
+                        tma_load_3d(b_dst, &tmB, bar, kk, n0, bbt);
+                    }
+                    if (++stage == (uint32_t)g.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, g.BN, g.a_mn, g.b_mn);
+            const uint32_t a_kstep = g.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
+            const uint32_t b_kstep = g.b_mn ? 2048u : 32u;
+            const uint32_t a_lbo = g.a_mn ? kGroupBytes : 16u;
+            const uint32_t b_lbo = g.b_mn ? kGroupBytes : 16u;
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(g, t);
+                mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kAccStride;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t a_base = tiles_base + stage * g.stage_bytes;
+                    const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024u);
+                        const uint64_t bd = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024u);
+                        umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (++stage == (uint32_t)g.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(&tfull_bar[as]));
+                as ^= 1u;
+                if (as == 0) aphase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;  // TMEM lane quarter == warp id % 4
+        uint32_t as = 0, aphase = 0;
+        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(g, t);
+            const int m = tc.tm * BM + q * 32 + lane;
+            const int n0 = tc.tn * g.BN;
+            const bool row_ok = m < g.M;
+            const long long crow = g.row_remap > 0 ? (long long)m + m / g.row_remap + 1 : (long long)m;
+            float bias_m = 0.f;
+            if (g.bias_mode == MC_BIAS_M && row_ok) bias_m = g.bias[m];
+            mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
+            for (int c = 0; c < g.BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c, v);
+                tmem_ld_wait();
+                const int nb = n0 + c;
+                if (row_ok && nb < g.N) {
+                    const int rem = g.N - nb;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const int ncols = rem - j8 * 8;
+                        if (ncols > 0) {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j8 * 8 + j]);
+                            epilogue8(g, x, bias_m, crow, tc.b, nb + j8 * 8, ncols, g.vec_ok && ncols >= 8);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+            as ^= 1u;
+            if (as == 0) aphase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// operand with logical [batch][rows][K]; see header for major / ld / batch_stride.
+int make_operand_map(CUtensorMap* map, const void* ptr, int major, int64_t rows, int64_t K, int64_t ld,
+                     int64_t batch, int64_t batch_stride, int box_rows, const char* name) {
+    EncodeTiledFn enc = get_encode_fn();
+    MC_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    MC_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm %s: base pointer must be 16-byte aligned", name);
+    MC_CHECK((ld * 2) % 16 == 0, "gemm %s: leading dimension %lld (bf16) must be a multiple of 8 elements", name,
+             (long long)ld);
+    MC_CHECK(batch_stride == 0 || (batch_stride * 2) % 16 == 0, "gemm %s: batch stride must be a multiple of 8", name);
+    const bool batched = batch_stride != 0 && batch > 1;
+    cuuint64_t gdim[3], gstride[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    if (major == MC_MAJOR_K) {
+        gdim[0] = (cuuint64_t)K;
+        gdim[1] = (cuuint64_t)rows;
+        box[0] = BK;
+        box[1] = (cuuint32_t)box_rows;
+    } else {
+        gdim[0] = (cuuint64_t)rows;
+        gdim[1] = (cuuint64_t)K;
+        box[0] = 64;
+        box[1] = BK;
+    }
+    gdim[2] = batched ? (cuuint64_t)batch : 1;
+    box[2] = 1;
+    gstride[0] = (cuuint64_t)ld * 2;
+    gstride[1] = batched ? (cuuint64_t)batch_stride * 2 : gstride[0] * gdim[1];
+    MC_CHECK(gdim[0] >= 1 && gdim[1] >= 1, "gemm %s: empty operand", name);
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MC_CHECK(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled(%s) failed with %d (dims %llu,%llu,%llu strides %llu,%llu box %u,%u)", name,
+             (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+             (unsigned long long)gstride[0], (unsigned long long)gstride[1], box[0], box[1]);
+    return MC_OK;
+}
+
+// Modelled cost (cycles, arbitrary unit) of running the problem with a given BN / split.
+double model_cost(int64_t M, int64_t N, int64_t out_batch, int64_t kb_total, int BN, int split, int sms, int heavy_epi) {
+    const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN) * out_batch * split;
+    const int64_t rounds = ceil_div(tiles, sms);
+    const double kb = double(kb_total) / split;
+    const double t_mma = 4.0 * (BN / 2.0 > (128 + BN) / 4.0 ? BN / 2.0 : (128 + BN) / 4.0);
+    const double epi = BN * (heavy_epi ? 16.0 : 6.0);
+    double tile = kb * t_mma;
+    if (epi > tile) tile = epi;  // epilogue of tile i overlaps the MMAs of tile i+1
+    return rounds * (tile + 600.0) + epi + 2500.0;
+}
+
+}  // namespace
+
+}  // namespace mc
+
+using namespace mc;
+
+extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MC_CHECK(p != nullptr, "null params");
+    MC_CHECK(p->M > 0 && p->N > 0 && p->K > 0 && p->batch > 0, "gemm: empty problem M=%lld N=%lld K=%lld batch=%lld",
+             (long long)p->M, (long long)p->N, (long long)p->K, (long long)p->batch);
+    MC_CHECK(p->M < (1ll << 31) && p->N < (1ll << 31) && p->K < (1ll << 31), "gemm: dimension too large");
+    MC_CHECK(p->A && p->B && p->C, "gemm: null operand");
+    MC_CHECK(p->c_dtype == MC_F32 || p->c_dtype == MC_BF16, "gemm: bad c_dtype");
+    MC_CHECK(!(p->accumulate && p->c_dtype != MC_F32), "gemm: accumulate needs fp32 C");
+    MC_CHECK(p->act != MC_ACT_GELU_BWD || p->zin != nullptr, "gemm: GELU_BWD needs zin");
+    MC_CHECK(p->bias_mode == MC_BIAS_NONE || p->bias != nullptr, "gemm: bias_mode set without bias");
+
+    GemmTcArgs g{};
+    g.M = (int)p->M; g.N = (int)p->N; g.K = (int)p->K;
+    g.k_spans_batch = p->k_spans_batch ? 1 : 0;
+    g.out_batch = g.k_spans_batch ? 1 : (int)p->batch;
+    g.kb_per_batch = (int)ceil_div(p->K, BK);
+    g.kb_total = g.kb_per_batch * (g.k_spans_batch ? (int)p->batch : 1);
+    g.a_mn = p->a_major == MC_MAJOR_MN; g.b_mn = p->b_major == MC_MAJOR_MN;
+    g.a_batched = (p->a_batch_stride != 0 && p->batch > 1); g.b_batched = (p->b_batch_stride != 0 && p->batch > 1);
+
+    const int sms = sm_count();
+    const bool linear_epi = p->act == MC_ACT_NONE && p->zout == nullptr && p->R == nullptr &&
+                            p->bias_mode == MC_BIAS_NONE && p->c_dtype == MC_F32 && p->accumulate;
+    const int heavy = p->act != MC_ACT_NONE;
+    // tile width / split-K selection by a small cost model (wave quantisation dominates at these sizes)
+    int best_bn = 0, best_split = 1;
+    double best = 1e300;
+    const int n_cap = (int)(ceil_div(p->N, 32) * 32);
+    for (int bn = 256; bn >= 32; bn -= 32) {
+        if (bn > n_cap && bn != 32) continue;
+        int max_split = 1;
+        if (p->split_k > 1) max_split = (int)p->split_k;
+        else if (p->split_k == 0 && linear_epi) max_split = 64;
+        for (int sp = (p->split_k > 1 ? max_split : 1); sp <= max_split; sp *= 2) {
+            if (sp > g.kb_total) break;
+            double c = model_cost(p->M, p->N, g.out_batch, g.kb_total, bn, sp, sms, heavy);
+            if (sp > 1) c += 800.0;  // atomics
+            if (c < best) { best = c; best_bn = bn; best_split = sp; }
+        }
+    }
+    MC_CHECK(best_bn > 0, "gemm: no tile configuration");
+    if (best_split > 1) MC_CHECK(linear_epi || p->split_k > 1, "gemm: split-K needs a linear fp32 accumulate epilogue");
+    g.BN = best_bn;
+    g.split_k = best_split;
+    g.tiles_m = (int)ceil_div(p->M, BM);
+    g.tiles_n = (int)ceil_div(p->N, g.BN);
+    const long long nt = (long long)g.tiles_m * g.tiles_n * g.out_batch * g.split_k;
+    MC_CHECK(nt < (1ll << 31), "gemm: too many tiles");
+    g.num_tiles = (int)nt;
+    g.b_tx_bytes = g.b_mn ? (int)(ceil_div(g.BN, 64) * kGroupBytes) : g.BN * BK * 2;
+    g.stage_bytes = (int)(kABytes + ceil_div(g.b_tx_bytes, 1024) * 1024);
+    const int smem_budget = 200 * 1024;
+    g.stages = smem_budget / g.stage_bytes;
+    if (g.stages > kMaxStages) g.stages = kMaxStages;
+    MC_CHECK(g.stages >= 2, "gemm: not enough shared memory for 2 stages");
+    // Always request >= 114 KB so that at most one CTA is resident per SM (each allocates all of TMEM).
+    const size_t smem = (size_t)g.stages * g.stage_bytes + 1024;
+
+    g.C = p->C; g.c_bf16 = p->c_dtype == MC_BF16; g.ldc = p->ldc; g.c_bs = p->c_batch_stride;
+    g.accumulate = p->accumulate; g.atomic = g.split_k > 1; g.row_remap = p->row_remap;
+    g.bias = p->bias; g.bias_mode = p->bias_mode;
+    g.zout = reinterpret_cast<__nv_bfloat16*>(p->zout); g.ldz = p->ldz; g.z_bs = p->z_batch_stride;
+    g.zin = reinterpret_cast<const __nv_bfloat16*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
+    g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
+    // vector (8-column) epilogue accesses need every touched row start to be 32-byte aligned
+    auto al = [](const void* q, long long ld, long long bs, int esz) {
+        return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 32 == 0) && (ld * esz) % 32 == 0 && (bs * esz) % 32 == 0);
+    };
+    g.vec_ok = al(p->C, p->ldc, p->c_batch_stride, g.c_bf16 ? 2 : 4) && al(p->zout, p->ldz, p->z_batch_stride, 2) &&
+               al(p->zin, p->ldzin, p->zin_batch_stride, 2) && al(p->R, p->ldr, p->r_batch_stride, 4) &&
+               (p->bias_mode != MC_BIAS_N || reinterpret_cast<uintptr_t>(p->bias) % 32 == 0) && (g.BN % 32 == 0);
+
+    CUtensorMap tmA, tmB;
+    int rc = make_operand_map(&tmA, p->A, p->a_major, p->M, p->K, p->lda, p->batch, p->a_batch_stride, BM, "A");
+    if (rc != MC_OK) return rc;
+    rc = make_operand_map(&tmB, p->B, p->b_major, p->N, p->K, p->ldb, p->batch, p->b_batch_stride, g.BN, "B");
+    if (rc != MC_OK) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_set = true;
+    }
+    const int grid = g.num_tiles < sms ? g.num_tiles : sms;
+    const size_t smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
+    gemm_tc_kernel<<<grid, kThreads, smem_req, stream>>>(tmA, tmB, g);
+    MC_CUDA(cudaGetLastError());
+    return MC_OK;
+}

@@ -1,0 +1,190 @@
+/* libmixerclip -- C ABI of the B200-native Mixer-CLIP training hot path.
+ *
+ * The reference (corentin-ryr/CLIP-mixer) is pure Python/PyTorch and has no FFI; this is the
+ * boundary a maintainer would bind (ctypes stub in INTEGRATION.md).  Every entry point replaces a
+ * group of library-call sites of the reference, cited per function as training/...:line.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller
+ *     (PyTorch's caching allocator); the library never allocates or frees device memory;
+ *   - every function launches asynchronously on `stream` (a cudaStream_t passed as void*) and
+ *     never synchronises, so the calls are CUDA-graph capturable;
+ *   - return 0 on success, a negative MC_ERR_* otherwise; mc_last_error() gives the message of
+ *     the last failure on the calling thread.  No exception crosses the boundary;
+ *   - "act" tensors are the GEMM operand copies: bf16 for the tensor-core engine, fp32 for the
+ *     SIMT validation engine.  The residual stream, LayerNorm statistics, gradients of
+ *     parameters, features and the contrastive head are always fp32.
+ */
+#ifndef MIXERCLIP_H_
+#define MIXERCLIP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_OK 0
+#define MC_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define MC_ERR_CUDA (-2)    /* a CUDA runtime / driver call failed */
+
+#define MC_F32 0
+#define MC_BF16 1
+
+#define MC_MAJOR_K 0  /* the K (reduction) index is contiguous in memory */
+#define MC_MAJOR_MN 1 /* the M (for A) / N (for B) index is contiguous in memory */
+
+#define MC_BIAS_NONE 0
+#define MC_BIAS_N 1 /* bias[n] added to every row    (nn.Linear on rows)         */
+#define MC_BIAS_M 2 /* bias[m] added to every column (token-mixing orientation)  */
+
+#define MC_ACT_NONE 0
+#define MC_ACT_GELU 1     /* QuickGELU, model.py:175-177                         */
+#define MC_ACT_GELU_BWD 2 /* multiply by QuickGELU'(zin[m,n])                     */
+
+int mc_version(void);
+const char* mc_last_error(void);
+/* sm count / compute capability of the current device */
+int mc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched GEMM with fused epilogue:  for every batch b
+ *     acc[m,n] = sum_k A_b[m,k] * B_b[n,k]
+ *     x = acc (+ bias)            ; optional store of x to zout (pre-activation, act dtype)
+ *     x = act(x)                  ; GELU, or x * GELU'(zin[m,n])
+ *     x = x + R_b[m,n]            ; optional fp32 residual
+ *     C_b[m',n] (=, += or atomic+=) x        with m' = m (+ m / row_remap + 1 if row_remap > 0)
+ * Replaces the cuBLAS/ATen call sites k1, k4-k11, k16 of SURVEY.md 2.4:
+ *   nn.Linear lin1..lin4 + QuickGELU + residual   training/clip/model.py:206-222
+ *   patch convolution as an im2col GEMM           training/clip/model.py:258,272
+ *   x @ proj, x @ text_projection                 training/clip/model.py:288,424
+ *   and the dgrad / wgrad GEMMs autograd derives from them (training/training.py:170).
+ *
+ * Operand A is logically [batch][M][K], B is [batch][N][K]; `*_major` says which logical index is
+ * contiguous, `ld*` is the element stride of the other index, `*_batch_stride` the element stride
+ * between batches (0 = shared).  With k_spans_batch != 0 the reduction also runs over the batch
+ * index (weight gradients of the token-mixing MLP: K = batch x D) and C has no batch dimension.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mc_gemm_params {
+    int64_t M, N, K, batch;
+    const void* A;
+    int32_t a_major;
+    int64_t lda, a_batch_stride;
+    const void* B;
+    int32_t b_major;
+    int64_t ldb, b_batch_stride;
+    int32_t k_spans_batch;
+    /* output */
+    void* C;
+    int32_t c_dtype; /* MC_F32 or MC_BF16 (act dtype engines only write their own act dtype or fp32) */
+    int64_t ldc, c_batch_stride;
+    int32_t accumulate; /* C += x (fp32 C only) */
+    int32_t split_k;    /* >1: K is split over CTAs and C is updated with atomic adds (fp32 C, implies +=) */
+    int32_t row_remap;  /* >0: destination row = m + m / row_remap + 1 (patch rows behind a class token) */
+    /* epilogue */
+    const float* bias;
+    int32_t bias_mode;
+    void* zout; /* act dtype, same shape as C */
+    int64_t ldz, z_batch_stride;
+    const void* zin; /* act dtype */
+    int64_t ldzin, zin_batch_stride;
+    int32_t act;
+    const float* R;
+    int64_t ldr, r_batch_stride;
+} mc_gemm_params;
+
+/* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory. */
+int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream);
+/* SIMT FFMA engine: fp32 operands (the 1e-5 validation precision of north_star). */
+int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm (always fp32 math), training/clip/model.py:166-172; instances ln_pre :263,
+ * layerNorm1/2 :205,210, ln_post :268, ln_final :344.
+ *   row r reads x + (row_index ? row_index[r] : r) * x_row_stride; rows with
+ *   r % cls_period == 0 read `cls` instead when cls != NULL (class token of model.py:275-277).
+ *   Writes y (y_dtype, dense [rows, D], or strided by y_row_stride) and mean / rstd [rows].
+ * ------------------------------------------------------------------------------------------ */
+int mc_ln_fwd(const float* x, int64_t x_row_stride, const int32_t* row_index, const float* cls, int64_t cls_period,
+              const float* gamma, const float* beta, void* y, int32_t y_dtype, int64_t y_row_stride, float* mean,
+              float* rstd, int64_t rows, int64_t D, void* stream);
+
+/* LayerNorm backward fused with the residual-gradient add and the reductions that ride on it:
+ *   dx[r] = (dres ? dres[r] : 0) + LNbwd(dy[r])           (fp32, plus an optional act copy dx_act)
+ *   dgamma += sum_r dy*xhat ; dbeta += sum_r dy           (atomic accumulation into fp32 [D])
+ *   colsum_out[d]   += sum_r dx[r,d]                      (bias grad of the preceding lin4, may be NULL)
+ *   rowsum_out[r%P] += sum_d dx[r,d]                      (bias grad of token-mix lin2, may be NULL)
+ * x rows are addressed like mc_ln_fwd (row_index / x_row_stride); dx rows likewise
+ * (dx_row_stride); dy is dense [rows, D] fp32.  Rows with r % cls_period == 0 (cls != NULL) take
+ * x from `cls` and accumulate their dx into dcls[D] instead of writing dx. */
+int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, const int32_t* row_index, const float* cls,
+              int64_t cls_period, const float* mean, const float* rstd, const float* gamma, const float* dres,
+              float* dx, int64_t dx_row_stride, void* dx_act, int32_t act_dtype, float* dgamma, float* dbeta,
+              float* colsum_out, float* rowsum_out, int64_t rowsum_period, float* dcls, int64_t rows, int64_t D,
+              void* stream);
+
+/* Column sums (bias grads of lin3, model.py:212) and per-row-group sums (bias grads of lin1):
+ *   colsum:  out[c] += sum_r x[r, c]                      x: [rows, cols] act dtype
+ *   rowsum:  out[r % period] += sum_c x[r, c]                                                */
+int mc_colsum(const void* x, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+int mc_rowsum(const void* x, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t period, float* out,
+              void* stream);
+
+/* fp32 -> act copy (dst dense), optional pad of the leading dimension (token-mix weights). */
+int mc_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t src_ld, void* dst, int32_t dst_dtype,
+                int64_t dst_ld, void* stream);
+
+/* im2col of the stride==kernel patch convolution, model.py:258,272:
+ *   image [B,3,R,R] (fp32, or uint8 with the /255 + Normalize of training.py:115,149 fused) ->
+ *   act [B*g*g, 3*p*p], row (b,gy,gx), column (c,py,px). */
+int mc_im2col(const void* image, int32_t image_is_u8, int64_t B, int64_t R, int64_t patch, void* out,
+              int32_t out_dtype, void* stream);
+
+/* Token embedding, model.py:414: x[b,t,:] = table[text[b,t],:]; and its gradient (run-length
+ * pre-reduced scatter-add: padding tokens repeat). text is int64 [B, C]. */
+int mc_embed_fwd(const int64_t* text, const float* table, float* x, int64_t B, int64_t C, int64_t W, int64_t vocab,
+                 void* stream);
+int mc_embed_bwd(const int64_t* text, const float* dx, float* dtable, int64_t B, int64_t C, int64_t W, int64_t vocab,
+                 void* stream);
+/* eot_row[b] = b*C + argmax_t text[b,t]  (first maximum, like torch.argmax; model.py:424) */
+int mc_eot_rows(const int64_t* text, int32_t* eot_row, int64_t B, int64_t C, void* stream);
+
+/* L2 normalisation of the features, model.py:433-434, and its backward
+ *   u = f / ||f||;   df = (du - u (u.du)) / ||f|| */
+int mc_l2norm_fwd(const float* f, float* u, float* inv_norm, int64_t rows, int64_t E, void* stream);
+int mc_l2norm_bwd(const float* du, const float* u, const float* inv_norm, float* df, void* df_act, int32_t act_dtype,
+                  int64_t rows, int64_t E, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Contrastive head, training/training.py:158-168 (+ its backward through autograd, :170), with
+ * the gathered features detached: two row-softmax cross-entropies over [n x N] logits that are
+ * never written to memory (online softmax over column tiles).
+ *   ui, ut     [n, E]  local normalised features;  ui_all, ut_all [N, E] gathered (rank order)
+ *   log_scale  device scalar t (logit_scale parameter); labels g_i = rank*n + i
+ * Outputs (fp32): loss[1] (+=, pre-zeroed by the caller), dui, dut [n, E] (overwritten),
+ *   dlog_scale[1] (+=), all already divided for the mean over n and the /2.
+ * workspace: mc_head_workspace_bytes(n, N, E) bytes.
+ * ------------------------------------------------------------------------------------------ */
+int64_t mc_head_workspace_bytes(int64_t n, int64_t N, int64_t E);
+int mc_head_fwd_bwd(const float* ui, const float* ut, const float* ui_all, const float* ut_all, const float* log_scale,
+                    int64_t n, int64_t N, int64_t E, int64_t rank, float grad_scale, float* loss, float* dui,
+                    float* dut, float* dlog_scale, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step of training/training.py:73-82,181,185 over flat fp32 buffers:
+ *   mc_sumsq: out[0] += sum g^2           (global grad norm for clip_grad_norm_(.., 20))
+ *   mc_adamw: g' = g * grad_mul * min(1, max_norm / (sqrt(sumsq[0]) * grad_mul + 1e-6));
+ *             AdamW (decoupled decay on the 64-element chunks whose decay_flags byte is 1);
+ *             optional bf16 mirror of the new weights.  The per-step scalars come from DEVICE
+ *             memory so a captured CUDA graph can be replayed while the schedule advances:
+ *             hyper = {lr, 1 - beta1^t, 1 - beta2^t}.  sumsq may be NULL (no clipping).
+ * ------------------------------------------------------------------------------------------ */
+int mc_sumsq(const float* g, int64_t n, float* out, void* stream);
+int mc_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const uint8_t* decay_flags, int64_t n,
+             const float* sumsq, const float* hyper, float grad_mul, float max_norm, float beta1, float beta2,
+             float eps, float weight_decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXERCLIP_H_ */
