@@ -1,0 +1,198 @@
+"""Thin tensor-level wrappers over the C ABI (include/mixerclip.h).
+
+Every function takes CUDA tensors, passes raw device pointers + the current CUDA stream to
+libmixerclip.so and returns nothing: outputs are written into caller-provided tensors (the
+library never allocates).  A non-CUDA tensor raises; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_NONE, F32, MAJOR_K, MAJOR_MN,
+                   GemmParams, MixerClipError, check)
+
+__all__ = ["gemm", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
+           "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "adamw", "device_info",
+           "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
+           "ACT_GELU_BWD", "launch_count", "reset_launch_count"]
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of libmixerclip kernel-launching calls made so far (bench.py's gpu_launches)."""
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MixerClipError("libmixerclip ops need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise MixerClipError(f"unsupported dtype {t.dtype}") from None
+
+
+def device_info():
+    lib = _lib.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib.mc_device_info(C.byref(a), C.byref(b), C.byref(c)), "mc_device_info")
+    return a.value, b.value, c.value
+
+
+def gemm(engine: str, M: int, N: int, K: int, batch: int,
+         A: torch.Tensor, a_major: int, lda: int, a_bs: int,
+         B: torch.Tensor, b_major: int, ldb: int, b_bs: int,
+         Cout: torch.Tensor, ldc: int, c_bs: int = 0, *,
+         k_spans_batch: bool = False, accumulate: bool = False, split_k: int = 1, row_remap: int = 0,
+         bias: Optional[torch.Tensor] = None, bias_mode: int = BIAS_NONE,
+         zout: Optional[torch.Tensor] = None, ldz: int = 0, z_bs: int = 0,
+         zin: Optional[torch.Tensor] = None, ldzin: int = 0, zin_bs: int = 0,
+         act: int = ACT_NONE, R: Optional[torch.Tensor] = None, ldr: int = 0, r_bs: int = 0):
+    """acc[m,n] = sum_k A[b][m,k] B[b][n,k] with the fused epilogue of mc_gemm_params.
+
+    engine "tc"   -> mc_gemm_bf16_tc  (A, B, zout, zin bf16)
+    engine "simt" -> mc_gemm_f32_simt (everything fp32)
+    """
+    lib = _lib.load()
+    want = torch.bfloat16 if engine == "tc" else torch.float32
+    for name, t in (("A", A), ("B", B), ("zout", zout), ("zin", zin)):
+        if t is not None and t.dtype != want:
+            raise MixerClipError(f"gemm[{engine}]: operand {name} must be {want}, got {t.dtype}")
+    for name, t in (("bias", bias), ("R", R)):
+        if t is not None and t.dtype != torch.float32:
+            raise MixerClipError(f"gemm: {name} must be fp32")
+    p = GemmParams()
+    p.M, p.N, p.K, p.batch = M, N, K, batch
+    p.A, p.a_major, p.lda, p.a_batch_stride = _ptr(A), a_major, lda, a_bs
+    p.B, p.b_major, p.ldb, p.b_batch_stride = _ptr(B), b_major, ldb, b_bs
+    p.k_spans_batch = 1 if k_spans_batch else 0
+    p.C, p.c_dtype, p.ldc, p.c_batch_stride = _ptr(Cout), dtype_code(Cout), ldc, c_bs
+    p.accumulate, p.split_k, p.row_remap = (1 if accumulate else 0), split_k, row_remap
+    p.bias, p.bias_mode = _ptr(bias), bias_mode
+    p.zout, p.ldz, p.z_batch_stride = _ptr(zout), ldz, z_bs
+    p.zin, p.ldzin, p.zin_batch_stride = _ptr(zin), ldzin, zin_bs
+    p.act = act
+    p.R, p.ldr, p.r_batch_stride = _ptr(R), ldr, r_bs
+    fn = lib.mc_gemm_bf16_tc if engine == "tc" else lib.mc_gemm_f32_simt
+    check(fn(C.byref(p), _stream()), f"mc_gemm[{engine}] M={M} N={N} K={K} batch={batch}")
+    _count()
+
+
+def ln_fwd(x, x_row_stride, gamma, beta, y, y_row_stride, mean, rstd, rows, D, *, row_index=None, cls=None,
+           cls_period=0):
+    check(_lib.load().mc_ln_fwd(_ptr(x), x_row_stride, _ptr(row_index), _ptr(cls), cls_period, _ptr(gamma), _ptr(beta),
+                                _ptr(y), dtype_code(y), y_row_stride, _ptr(mean), _ptr(rstd), rows, D, _stream()),
+          "mc_ln_fwd")
+    _count()
+
+
+def ln_bwd(dy, x, x_row_stride, mean, rstd, gamma, dx, dx_row_stride, dgamma, dbeta, rows, D, *, row_index=None,
+           cls=None, cls_period=0, dres=None, dx_act=None, colsum_out=None, rowsum_out=None, rowsum_period=0,
+           dcls=None):
+    act_code = dtype_code(dx_act) if dx_act is not None else F32
+    check(_lib.load().mc_ln_bwd(_ptr(dy), _ptr(x), x_row_stride, _ptr(row_index), _ptr(cls), cls_period, _ptr(mean),
+                                _ptr(rstd), _ptr(gamma), _ptr(dres), _ptr(dx), dx_row_stride, _ptr(dx_act), act_code,
+                                _ptr(dgamma), _ptr(dbeta), _ptr(colsum_out), _ptr(rowsum_out), rowsum_period,
+                                _ptr(dcls), rows, D, _stream()), "mc_ln_bwd")
+    _count()
+
+
+def colsum(x, rows, cols, ld, out):
+    check(_lib.load().mc_colsum(_ptr(x), dtype_code(x), rows, cols, ld, _ptr(out), _stream()), "mc_colsum")
+    _count()
+
+
+def rowsum(x, rows, cols, ld, period, out):
+    check(_lib.load().mc_rowsum(_ptr(x), dtype_code(x), rows, cols, ld, period, _ptr(out), _stream()), "mc_rowsum")
+    _count()
+
+
+def cast_pad(src, rows, cols, src_ld, dst, dst_ld):
+    check(_lib.load().mc_cast_pad(_ptr(src), rows, cols, src_ld, _ptr(dst), dtype_code(dst), dst_ld, _stream()),
+          "mc_cast_pad")
+    _count()
+
+
+def im2col(image, B, R, patch, out):
+    if image.dtype not in (torch.float32, torch.uint8):
+        raise MixerClipError(f"im2col: image must be fp32 or uint8, got {image.dtype}")
+    check(_lib.load().mc_im2col(_ptr(image), 1 if image.dtype == torch.uint8 else 0, B, R, patch, _ptr(out),
+                                dtype_code(out), _stream()), "mc_im2col")
+    _count()
+
+
+def embed_fwd(text, table, x, B, Cn, W, vocab):
+    check(_lib.load().mc_embed_fwd(_ptr(text), _ptr(table), _ptr(x), B, Cn, W, vocab, _stream()), "mc_embed_fwd")
+    _count()
+
+
+def embed_bwd(text, dx, dtable, B, Cn, W, vocab):
+    check(_lib.load().mc_embed_bwd(_ptr(text), _ptr(dx), _ptr(dtable), B, Cn, W, vocab, _stream()), "mc_embed_bwd")
+    _count()
+
+
+def eot_rows(text, out, B, Cn):
+    check(_lib.load().mc_eot_rows(_ptr(text), _ptr(out), B, Cn, _stream()), "mc_eot_rows")
+    _count()
+
+
+def l2norm_fwd(f, u, inv_norm, rows, E):
+    check(_lib.load().mc_l2norm_fwd(_ptr(f), _ptr(u), _ptr(inv_norm), rows, E, _stream()), "mc_l2norm_fwd")
+    _count()
+
+
+def l2norm_bwd(du, u, inv_norm, df, df_act, rows, E):
+    act_code = dtype_code(df_act) if df_act is not None else F32
+    check(_lib.load().mc_l2norm_bwd(_ptr(du), _ptr(u), _ptr(inv_norm), _ptr(df), _ptr(df_act), act_code, rows, E,
+                                    _stream()), "mc_l2norm_bwd")
+    _count()
+
+
+def head_workspace_bytes(n, N, E) -> int:
+    return int(_lib.load().mc_head_workspace_bytes(n, N, E))
+
+
+def head_fwd_bwd(ui, ut, ui_all, ut_all, log_scale, n, N, E, rank, grad_scale, loss, dui, dut, dlog_scale, workspace):
+    check(_lib.load().mc_head_fwd_bwd(_ptr(ui), _ptr(ut), _ptr(ui_all), _ptr(ut_all), _ptr(log_scale), n, N, E, rank,
+                                      float(grad_scale), _ptr(loss), _ptr(dui), _ptr(dut), _ptr(dlog_scale),
+                                      _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()),
+          "mc_head_fwd_bwd")
+    _count(2)
+
+
+def sumsq(g, n, out):
+    check(_lib.load().mc_sumsq(_ptr(g), n, _ptr(out), _stream()), "mc_sumsq")
+    _count()
+
+
+def adamw(p, g, m, v, p_bf16, decay_flags, n, sumsq_buf, hyper, grad_mul, max_norm, beta1, beta2, eps, weight_decay):
+    check(_lib.load().mc_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), _ptr(decay_flags), n, _ptr(sumsq_buf),
+                               _ptr(hyper), float(grad_mul), float(max_norm), float(beta1), float(beta2), float(eps),
+                               float(weight_decay), _stream()), "mc_adamw")
+    _count()
