@@ -18,6 +18,8 @@
 // Out-of-bounds parts of a box are zero-filled by TMA, so ragged M/N/K (50, 77, 197, 200, 308 ...)
 // need no padding copies of the activations; only rows whose byte pitch is not a multiple of 16 B
 // (token-mix weights) are re-packed by mc_cast_pad.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mc {
@@ -46,9 +48,9 @@ struct GemmTcArgs {
     int accumulate, atomic, row_remap, vec_ok;
     const float* bias;
     int bias_mode;
-    __nv_bfloat16* zout;
+    __half* zout;  // pre-activations are private to this engine: fp16 (11-bit mantissa), see DESIGN.md
     long long ldz, z_bs;
-    const __nv_bfloat16* zin;
+    const __half* zin;
     long long ldzin, zin_bs;
     int act;
     const float* R;
@@ -72,6 +74,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcArgs& g, int t) {
     return c;
 }
 
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+
 // ---- epilogue on 8 consecutive columns held in registers ----------------------------------------
 __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], float bias_m, long long crow, int b,
                                           int n, int ncols, bool vec) {
@@ -93,16 +103,16 @@ __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], fl
     }
     // pre-activation store
     if (g.zout != nullptr) {
-        __nv_bfloat16* zp = g.zout + (long long)b * g.z_bs + crow * g.ldz + n;
+        __half* zp = g.zout + (long long)b * g.z_bs + crow * g.ldz + n;
         if (vec) {
             uint4 pk;
-            pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
-            pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
+            pk.x = pack_h2(x[0], x[1]); pk.y = pack_h2(x[2], x[3]);
+            pk.z = pack_h2(x[4], x[5]); pk.w = pack_h2(x[6], x[7]);
             *reinterpret_cast<uint4*>(zp) = pk;
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (j < ncols) zp[j] = __float2bfloat16_rn(x[j]);
+                if (j < ncols) zp[j] = __float2half_rn(fminf(fmaxf(x[j], -65504.f), 65504.f));
         }
     }
     // activation
@@ -110,17 +120,18 @@ __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], fl
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = quick_gelu_fast(x[j]);
     } else if (g.act == MC_ACT_GELU_BWD) {
-        const __nv_bfloat16* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
+        const __half* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
         if (vec) {
             const uint4 pk = *reinterpret_cast<const uint4*>(zp);
-            x[0] *= quick_gelu_grad_fast(bf16_lo(pk.x)); x[1] *= quick_gelu_grad_fast(bf16_hi(pk.x));
-            x[2] *= quick_gelu_grad_fast(bf16_lo(pk.y)); x[3] *= quick_gelu_grad_fast(bf16_hi(pk.y));
-            x[4] *= quick_gelu_grad_fast(bf16_lo(pk.z)); x[5] *= quick_gelu_grad_fast(bf16_hi(pk.z));
-            x[6] *= quick_gelu_grad_fast(bf16_lo(pk.w)); x[7] *= quick_gelu_grad_fast(bf16_hi(pk.w));
+            const float2 z0 = unpack_h2(pk.x), z1 = unpack_h2(pk.y), z2 = unpack_h2(pk.z), z3 = unpack_h2(pk.w);
+            x[0] *= quick_gelu_grad_fast(z0.x); x[1] *= quick_gelu_grad_fast(z0.y);
+            x[2] *= quick_gelu_grad_fast(z1.x); x[3] *= quick_gelu_grad_fast(z1.y);
+            x[4] *= quick_gelu_grad_fast(z2.x); x[5] *= quick_gelu_grad_fast(z2.y);
+            x[6] *= quick_gelu_grad_fast(z3.x); x[7] *= quick_gelu_grad_fast(z3.y);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (j < ncols) x[j] *= quick_gelu_grad_fast(__bfloat162float(zp[j]));
+                if (j < ncols) x[j] *= quick_gelu_grad_fast(__half2float(zp[j]));
         }
     }
     // residual
@@ -472,8 +483,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.C = p->C; g.c_bf16 = p->c_dtype == MC_BF16; g.ldc = p->ldc; g.c_bs = p->c_batch_stride;
     g.accumulate = p->accumulate; g.atomic = g.split_k > 1; g.row_remap = p->row_remap;
     g.bias = p->bias; g.bias_mode = p->bias_mode;
-    g.zout = reinterpret_cast<__nv_bfloat16*>(p->zout); g.ldz = p->ldz; g.z_bs = p->z_batch_stride;
-    g.zin = reinterpret_cast<const __nv_bfloat16*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
+    g.zout = reinterpret_cast<__half*>(p->zout); g.ldz = p->ldz; g.z_bs = p->z_batch_stride;
+    g.zin = reinterpret_cast<const __half*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
     // vector (8-column) epilogue accesses need every touched row start to be 32-byte aligned
     auto al = [](const void* q, long long ld, long long bs, int esz) {

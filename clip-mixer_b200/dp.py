@@ -1,0 +1,147 @@
+"""Single-box data parallelism for the Mixer-CLIP step, one process per GPU over torch.distributed
+(NCCL on the GPUs, gloo in the CPU tests).  Replaces what ``accelerate`` does for the reference
+(third-party, un-vendored; call sites training/training.py:64,93-95,158-159,170):
+
+  * ``gather``: rank-ordered all_gather of the DETACHED normalised features along dim 0
+    (training.py:158-159), both towers in one [n, 2E] message;
+  * gradient averaging: DDP semantics (mean over ranks) on contiguous buckets of the flat gradient
+    buffer, each launched from the backward schedule as soon as its block is complete
+    (engine.TowerRT.backward -> after_block), on a side stream so it overlaps the remaining backward;
+  * labels: ``arange(n) + rank * n`` (training.py:165-167) - passed to the head kernel as ``rank``.
+
+The path shards by samples only (weights replicated): there is no other collective.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def bucket_index(tags: List[Tuple[str, object]]):
+    """(kind, tag) -> bucket number, in backward completion order (see CLIP._flat_order)."""
+    return {t: i for i, t in enumerate(tags)}
+
+
+class GradBucketReducer:
+    """Averages slices of one flat gradient tensor across ranks, bucket by bucket.
+
+    Works on any device/backend (the CPU tests drive it with gloo); on CUDA the all-reduces run on
+    ``comm_stream`` behind an event recorded on the compute stream at the call point.
+    """
+
+    def __init__(self, flat_g: torch.Tensor, ranges: List[Tuple[int, int]], group=None, min_bucket_elems: int = 0,
+                 close_after=()):
+        self.flat_g, self.group = flat_g, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cuda = flat_g.is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        # merge consecutive ranges until each bucket holds at least min_bucket_elems (launch-latency bound)
+        merged, cur_b, cur_e, members, cur_m = [], None, None, [], []
+        for i, (b, e) in enumerate(ranges):
+            if cur_b is None:
+                cur_b, cur_e, cur_m = b, e, [i]
+            else:
+                assert b == cur_e, "bucket ranges must be contiguous and in backward order"
+                cur_e = e
+                cur_m.append(i)
+            if cur_e - cur_b >= min_bucket_elems or i in close_after:
+                merged.append((cur_b, cur_e))
+                members.append(cur_m)
+                cur_b = None
+        if cur_b is not None:
+            merged.append((cur_b, cur_e))
+            members.append(cur_m)
+        self.buckets = merged
+        self.last_member = {m[-1]: k for k, m in enumerate(members)}   # original index that completes bucket k
+        self.pending = []
+        self.launched = 0
+
+    def ready(self, original_index: int):
+        """Original range ``original_index`` is complete; launch its (merged) bucket if it closes one."""
+        k = self.last_member.get(original_index)
+        if k is None or self.world == 1:
+            return
+        b, e = self.buckets[k]
+        view = self.flat_g[b:e]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            view.div_(self.world)
+        self.launched += 1
+
+    def finish(self):
+        """Make the compute stream wait for every launched all-reduce."""
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.launched = 0
+
+
+def gather_features(ui: torch.Tensor, ut: torch.Tensor, group=None):
+    """all_gather of [n, E] image and text features in ONE [n, 2E] message, rank order along dim 0,
+    no autograd through it (training.py:158-159).  Returns (ui_all, ut_all) of shape [N, E]."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ui.detach(), ut.detach()
+    world = dist.get_world_size(group)
+    n, E = ui.shape
+    packed = torch.cat([ui.detach(), ut.detach()], dim=1).contiguous()
+    out = torch.empty(world * n, 2 * E, device=ui.device, dtype=ui.dtype)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return out[:, :E].contiguous(), out[:, E:].contiguous()
+
+
+class DataParallel:
+    """Installs the bucketed gradient averaging on a CLIP model (``model._dp``) and exposes the
+    feature gather.  ``isinstance(x, DataParallel)`` plays the role of the reference's
+    ``isinstance(self.model, DistributedDataParallel)`` branch (training.py:174)."""
+
+    def __init__(self, model, group=None, min_bucket_mb: float = 8.0):
+        self.module, self.group = model, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        store = model._require_store()
+        store.ensure_grads()
+        self.index = bucket_index(model._bucket_tags)
+        # never merge across a tower boundary: autograd may run the two tower backwards in either order
+        close = {self.index[("text", "bottom")], self.index[("image", "bottom")]}
+        self.reducer = GradBucketReducer(store.flat_g, store.bucket_ranges, group,
+                                         min_bucket_elems=int(min_bucket_mb * (1 << 20) / 4), close_after=close)
+        model._dp = self
+
+    def after_block_hook(self, kind: str) -> Optional[Callable]:
+        if self.world == 1:
+            return None
+        return lambda tag: self.reducer.ready(self.index[(kind, tag)])
+
+    def gather(self, ui, ut):
+        return gather_features(ui, ut, self.group)
+
+    def finish(self):
+        """Call once per step after backward: reduces the tail bucket (logit_scale) and joins the streams."""
+        if self.world > 1:
+            self.reducer.ready(self.index[("head", "final")])
+        self.reducer.finish()
+
+    # nn.Module-like conveniences so the wrapper can stand where the DDP-wrapped model stood
+    def __call__(self, *a, **k):
+        return self.module(*a, **k)
+
+    def parameters(self):
+        return self.module.parameters()
+
+    def named_parameters(self):
+        return self.module.named_parameters()
+
+    def train(self, mode=True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.module.eval()
+        return self

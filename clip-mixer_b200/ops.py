@@ -81,9 +81,10 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
     """
     lib = _lib.load()
     want = torch.bfloat16 if engine == "tc" else torch.float32
-    for name, t in (("A", A), ("B", B), ("zout", zout), ("zin", zin)):
-        if t is not None and t.dtype != want:
-            raise MixerClipError(f"gemm[{engine}]: operand {name} must be {want}, got {t.dtype}")
+    zwant = torch.float16 if engine == "tc" else torch.float32
+    for name, t, w in (("A", A, want), ("B", B, want), ("zout", zout, zwant), ("zin", zin, zwant)):
+        if t is not None and t.dtype != w:
+            raise MixerClipError(f"gemm[{engine}]: operand {name} must be {w}, got {t.dtype}")
     for name, t in (("bias", bias), ("R", R)):
         if t is not None and t.dtype != torch.float32:
             raise MixerClipError(f"gemm: {name} must be fp32")

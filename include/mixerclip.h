@@ -84,16 +84,16 @@ typedef struct mc_gemm_params {
     /* epilogue */
     const float* bias;
     int32_t bias_mode;
-    void* zout; /* act dtype, same shape as C */
+    void* zout; /* pre-activation, same shape as C: fp16 for the tensor-core engine, fp32 for SIMT */
     int64_t ldz, z_batch_stride;
-    const void* zin; /* act dtype */
+    const void* zin; /* same format as zout */
     int64_t ldzin, zin_batch_stride;
     int32_t act;
     const float* R;
     int64_t ldr, r_batch_stride;
 } mc_gemm_params;
 
-/* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory. */
+/* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory; zout / zin fp16. */
 int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream);
 /* SIMT FFMA engine: fp32 operands (the 1e-5 validation precision of north_star). */
 int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream);

@@ -49,6 +49,7 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(seed)
     opd = torch.bfloat16 if engine == "tc" else torch.float32
+    zdt = torch.float16 if engine == "tc" else torch.float32
     ab = 1 if a_shared else batch
     bb = 1 if b_shared else batch
     A_log = torch.randn(ab, M, K, generator=g).to(dev)
@@ -79,7 +80,7 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
     if act == 1:
         x = _gelu(x)
     elif act == 2:
-        zin_log = torch.randn(ob, M, N, generator=g).to(dev).to(opd)
+        zin_log = torch.randn(ob, M, N, generator=g).to(dev).to(zdt)
         x = x * _gelu_grad(zin_log.double())
     R = None
     if residual:
@@ -96,14 +97,14 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
         return mem
 
     if act == 2:
-        zin = place(zin_log, opd)
+        zin = place(zin_log, zdt)
     if residual:
         R = place(R_log, torch.float32)
     cdt = torch.bfloat16 if c_bf16 else torch.float32
     C0 = torch.randn(ob, Mout, N, generator=g).to(dev).to(cdt) if (accumulate or split_k > 1) else \
         torch.full((ob, Mout, N), 7.0, device=dev, dtype=cdt)
     Cm = C0.clone()
-    Z = torch.full((ob, Mout, N), 7.0, device=dev, dtype=opd) if zout else None
+    Z = torch.full((ob, Mout, N), 7.0, device=dev, dtype=zdt) if zout else None
     ops.gemm(engine, M, N, K, batch, A_mem, a_major, lda, a_bs, B_mem, b_major, ldb, b_bs, Cm, N, Mout * N,
              k_spans_batch=k_spans, accumulate=accumulate, split_k=split_k, row_remap=row_remap, bias=bias,
              bias_mode=bias_mode, zout=Z, ldz=N, z_bs=Mout * N, zin=zin, ldzin=N, zin_bs=Mout * N, act=act, R=R,
@@ -124,7 +125,7 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
     if zout:
         ze = place(z_expected, torch.float64, fill=7.0)
         zerr = ((Z.double() - ze).abs().max() / scale).item()
-        assert zerr <= (2e-2 if engine == "tc" else 2e-5), f"zout mismatch {zerr:.3e}"
+        assert zerr <= (3e-3 if engine == "tc" else 2e-5), f"zout mismatch {zerr:.3e}"
 
 
 ENGINES = ["simt", "tc"]
