@@ -18,7 +18,7 @@ from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_
 __all__ = ["gemm", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
            "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "adamw", "device_info",
            "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
-           "ACT_GELU_BWD", "launch_count", "reset_launch_count"]
+           "ACT_GELU_BWD", "launch_count", "reset_launch_count", "enable_gemm_timing", "collect_gemm_timing"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 _launches = 0
@@ -37,6 +37,27 @@ def reset_launch_count():
 def _count(n=1):
     global _launches
     _launches += n
+
+
+_gemm_timing = None
+
+
+def enable_gemm_timing(on: bool):
+    """Instrumentation for bench.py: bracket every GEMM launch with CUDA events on the launching stream."""
+    global _gemm_timing
+    _gemm_timing = [] if on else None
+
+
+def collect_gemm_timing():
+    """[{engine, M, N, K, batch, flops, ms}] for the launches since enable_gemm_timing(True); synchronises."""
+    torch.cuda.synchronize()
+    out = []
+    for rec in (_gemm_timing or []):
+        out.append(dict(engine=rec[0], M=rec[1], N=rec[2], K=rec[3], batch=rec[4], flops=2.0 * rec[1] * rec[2] * rec[3] * rec[4],
+                        ms=rec[5].elapsed_time(rec[6]), tag=rec[7]))
+    if _gemm_timing is not None:
+        _gemm_timing.clear()
+    return out
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -101,7 +122,14 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
     p.act = act
     p.R, p.ldr, p.r_batch_stride = _ptr(R), ldr, r_bs
     fn = lib.mc_gemm_bf16_tc if engine == "tc" else lib.mc_gemm_f32_simt
+    if _gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(C.byref(p), _stream()), f"mc_gemm[{engine}] M={M} N={N} K={K} batch={batch}")
+    if _gemm_timing is not None:
+        e1.record()
+        tag = f"a{a_major}b{b_major}" + ("kb" if k_spans_batch else "") + (f"act{act}" if act else "")
+        _gemm_timing.append((engine, M, N, K, batch, e0, e1, tag))
     _count()
 
 

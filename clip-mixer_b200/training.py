@@ -1,0 +1,239 @@
+"""Training step and loop of the reference's ``training/training.py`` on the CUDA path.
+
+``FusedTrainStep`` is lines :144-186 of the reference loop (zero_grad -> forward -> gather(detach) ->
+logits / cross-entropy -> backward -> logit-scale clamp -> clip_grad_norm_ -> AdamW -> scheduler) as one
+explicit schedule over libmixerclip kernels, with no autograd graph, no host synchronisation (the
+reference's ``total_loss.item()`` at :190 is a per-step sync) and, optionally, captured once into a
+CUDA graph and replayed.
+
+``Trainer`` keeps the shape of the reference class (``Trainer(model, preprocess, epochs, args)``,
+``train()``, ``validate()``, ``save_model()``, ``load_model()``) on synthetic data: the Azure / LAION
+/ accelerate / TensorBoard scaffolding around the loop is out of scope (SURVEY 2.1 rows 8-10,12).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import MixerClipError
+from .dp import DataParallel
+from .optim import FusedAdamW, cosine_warmup_lr
+
+
+class FusedTrainStep:
+    """One optimisation step on a per-rank batch.  ``step(images, texts)`` returns the (device) loss of
+    this rank; nothing is read back to the host."""
+
+    def __init__(self, model, optimizer: Optional[FusedAdamW] = None, dp: Optional[DataParallel] = None,
+                 total_steps: int = 10 ** 9, max_lr: float = 5e-4, warmup_steps: int = 2, use_cuda_graph: bool = False):
+        self.model = model
+        self.dp = dp
+        self.world = dp.world if dp is not None else 1
+        self.rank = dp.rank if dp is not None else 0
+        store = model._require_store()
+        store.ensure_grads()
+        model._attach_grads()
+        self.store = store
+        self.opt = optimizer if optimizer is not None else FusedAdamW(model, lr=max_lr)
+        self.total_steps, self.max_lr, self.min_lr, self.warmup = total_steps, max_lr, max_lr / 100, warmup_steps
+        self.sched_step = 0
+        dev = store.device
+        self.loss = torch.zeros(1, device=dev)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+        self.static_images = self.static_texts = None
+        self._bufs = {}
+        self.clamp_ddp_branch = self.world > 1     # training.py:174-178 has two different clamps
+
+    # ---- schedule -----------------------------------------------------------------------------------
+    def current_lr(self):
+        return cosine_warmup_lr(self.sched_step, self.total_steps, self.max_lr, self.min_lr, self.warmup)
+
+    # ---- the device-side schedule (graph-capturable) ----------------------------------------------
+    def _device_step(self, images, texts):
+        model, store = self.model, self.store
+        prec = model._precision
+        img_t, txt_t = model._towers["image"], model._towers["text"]
+        n = images.shape[0]
+        E = model._cfg["embed_dim"]
+        store.flat_g.zero_()                                                        # optimizer.zero_grad()  :144
+        model._prepare_weights()
+        ws_i = img_t.forward(images, prec, True)                                    # model(images, texts)   :156
+        ws_t = txt_t.forward(texts, prec, True)
+        if self.dp is not None and self.world > 1:
+            ui_all, ut_all = self.dp.gather(ws_i.u_feat, ws_t.u_feat)               # accelerator.gather     :158-159
+        else:
+            ui_all, ut_all = ws_i.u_feat, ws_t.u_feat
+        N = ui_all.shape[0]
+        key = (n, N, E)
+        if key not in self._bufs:
+            dev = store.device
+            self._bufs = {key: dict(dui=torch.empty(n, E, device=dev), dut=torch.empty(n, E, device=dev),
+                                    ws=torch.empty(ops.head_workspace_bytes(n, N, E) // 4, device=dev))}
+        b = self._bufs[key]
+        self.loss.zero_()
+        ops.head_fwd_bwd(ws_i.u_feat, ws_t.u_feat, ui_all, ut_all, model.logit_scale, n, N, E, self.rank, 1.0,
+                         self.loss, b["dui"], b["dut"], store.grad_view("logit_scale"), b["ws"])   # :162-170
+        hook_t = self.dp.after_block_hook("text") if self.dp is not None else None
+        hook_i = self.dp.after_block_hook("image") if self.dp is not None else None
+        txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)                    # accelerator.backward   :170
+        img_t.backward(ws_i, b["dui"], prec, after_block=hook_i)
+        if self.dp is not None:
+            self.dp.finish()
+        with torch.no_grad():                                                       # clamp                  :173-178
+            if self.clamp_ddp_branch:
+                model.logit_scale.data.clamp_(0, math.log(100))
+            else:
+                model.logit_scale.data.clamp_(max=100)
+        self.opt.launch(grad_mul=1.0)                                               # clip + step            :181,185
+
+    def step(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
+        if not (images.is_cuda and texts.is_cuda):
+            raise MixerClipError("FusedTrainStep needs CUDA inputs (no CPU fallback)")
+        self.opt.set_step_scalars(self.current_lr())
+        if not self.use_graph:
+            self._device_step(images, texts)
+        else:
+            if self.graph is None:
+                self._capture(images, texts)
+            self.static_images.copy_(images, non_blocking=True)
+            self.static_texts.copy_(texts, non_blocking=True)
+            self.graph.replay()
+        self.model._trusted_mirror = True     # the optimizer kernel keeps the bf16 mirror current
+        self.sched_step += 1                                                        # scheduler.step()       :186
+        return self.loss
+
+    def _capture(self, images, texts):
+        self.static_images = images.clone()
+        self.static_texts = texts.to(torch.int64).clone()
+        # warm-up on a side stream (allocations, tensor maps, NCCL channels), restoring the weights after
+        snap_p = self.store.flat_p.clone()
+        snap_m, snap_v = self.opt.m.clone(), self.opt.v.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._device_step(self.static_images, self.static_texts)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.store.flat_p.copy_(snap_p)
+        self.opt.m.copy_(snap_m)
+        self.opt.v.copy_(snap_v)
+        if self.model._precision.act == torch.bfloat16:
+            self.store.refresh_mirror(force=True)
+        self.model._trusted_mirror = True     # do not bake a redundant cast pass into the graph
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._device_step(self.static_images, self.static_texts)
+
+
+# -------------------------------------------------------------------------------------------------
+# synthetic data and the reference-shaped Trainer
+# -------------------------------------------------------------------------------------------------
+def synthetic_batch(cfg: dict, batch: int, seed: int, device, uint8_images: bool = True):
+    """Throughput inputs of SURVEY 8-d: uint8 images (the loop's /255 + Normalize is fused into the patch
+    embedding), token rows SOT .. EOT 0 0 0 with a unique arg-max."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    R = cfg["image_resolution"]
+    if uint8_images:
+        images = torch.randint(0, 256, (batch, 3, R, R), dtype=torch.uint8, generator=g)
+    else:
+        images = torch.randn(batch, 3, R, R, generator=g)
+    C, V = cfg["context_length"], cfg["vocab_size"]
+    text = torch.randint(1, max(2, V - 2), (batch, C), generator=g)
+    text[:, 0] = V - 2
+    pos = torch.randint(1, C, (batch,), generator=g)
+    ar = torch.arange(C)[None, :]
+    text = torch.where(ar == pos[:, None], torch.full_like(text, V - 1), text)
+    text = torch.where(ar > pos[:, None], torch.zeros_like(text), text)
+    return images.to(device), text.to(device)
+
+
+class SyntheticPairs:
+    """Stands where ``LaionCoco`` + DataLoader stood (training.py:60-62): yields (images uint8, token ids)."""
+
+    def __init__(self, cfg, batch, steps, device, seed=1000):
+        self.cfg, self.batch, self.steps, self.device, self.seed = cfg, batch, steps, device, seed
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        for i in range(self.steps):
+            yield synthetic_batch(self.cfg, self.batch, self.seed + i, self.device)
+
+
+class Trainer:
+    """Shape of the reference's Trainer (training.py:30-250) over FusedTrainStep and synthetic data."""
+
+    def __init__(self, model, preprocess=None, epochs: int = 1, args=None, batch_size: int = 256,
+                 steps_per_epoch: int = 10, use_cuda_graph: bool = False):
+        self.epochs = epochs
+        self.model = model
+        self.preprocess = preprocess
+        self.runName = getattr(args, "run_name", "run") if args is not None else "run"
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if batch_size % self.world:
+            raise MixerClipError("global batch must divide by the number of ranks (split_batches, training.py:64)")
+        dev = model.logit_scale.device
+        self.trainLoader = SyntheticPairs(model._cfg, batch_size // self.world, steps_per_epoch, dev,
+                                          seed=1000 + self.rank * 100003)
+        self.numBatches = len(self.trainLoader)
+        self.dp = DataParallel(model) if self.world > 1 else None
+        self.optimizer = FusedAdamW(model, lr=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2, max_grad_norm=20.0)
+        self.stepper = FusedTrainStep(model, self.optimizer, self.dp, total_steps=self.epochs * self.numBatches,
+                                      max_lr=5e-4, warmup_steps=2, use_cuda_graph=use_cuda_graph)
+        self.startEpoch, self.currentStep = self.load_model()
+        self.losses = []
+
+    def train(self):
+        global_step = 0
+        for epoch in range(self.startEpoch, self.epochs):
+            self.model.train()
+            for idx, (images, texts) in enumerate(self.trainLoader):
+                if idx < self.currentStep:
+                    continue
+                global_step = epoch * self.numBatches + idx
+                loss = self.stepper.step(images, texts)
+                self.losses.append(loss.clone())          # device tensors: read after the loop, no per-step sync
+                self.currentStep = idx + 1
+                if global_step % 400 == 399:
+                    self.save_model(epoch, self.currentStep)
+                    self.validate(global_step)
+            self.currentStep = 0
+        self.validate(global_step)
+        return [float(l) for l in self.losses]
+
+    def validate(self, step):
+        """The reference runs ImageNetV2 / STS / MNIST / SST-2 validators here (training.py:211-216); they
+        need datasets that are not reachable offline.  The zero-shot scoring shape is in zeroshot.py."""
+        return None
+
+    def save_model(self, currentEpoch: int, currentStep: int = 0):
+        if self.rank == 0:
+            os.makedirs("outputs/checkpoints", exist_ok=True)
+            torch.save({"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
+                        "sched_step": self.stepper.sched_step}, "outputs/checkpoints/state.pt")
+            with open("outputs/checkpoints/epoch.json", "w") as f:
+                json.dump({"epoch": currentEpoch, "step": currentStep}, f)          # training.py:223
+        if dist.is_initialized():
+            dist.barrier()
+
+    def load_model(self):
+        try:
+            with open("outputs/checkpoints/epoch.json") as f:
+                meta = json.load(f)
+            st = torch.load("outputs/checkpoints/state.pt", map_location=self.model.logit_scale.device)
+            self.model.load_state_dict(st["model"])
+            self.optimizer.load_state_dict(st["optimizer"])
+            self.stepper.sched_step = st["sched_step"]
+            return meta["epoch"], meta["step"]
+        except Exception:                                                           # training.py:245-248
+            return 0, 0
