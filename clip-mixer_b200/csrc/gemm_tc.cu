@@ -5,10 +5,16 @@
 // residual, training/clip/model.py:206-222; conv1 as im2col GEMM :258,272; projections :288,424;
 // and the dgrad / wgrad GEMMs autograd derives from them, training/training.py:170).
 //
-//   warp 0   : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1   : MMA issuer     (one thread, tcgen05.mma kind::f16, 128 x BN x 16, fp32 accum in TMEM)
-//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
-//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> global)
+//   warp 0    : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1    : MMA issuer     (one thread, tcgen05.mma kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 2    : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warps 4-11: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> global,
+//                               256-bit global accesses; two warps per TMEM lane quarter, one per SMSP pair)
+//
+// These GEMMs are L2->SM bandwidth bound with a 128 x 256 tile (48 KB of operands per 64-deep k-block
+// against ~42 B/clk/SM of L2 bandwidth), so the kernel runs as 2-CTA clusters along M: the two CTAs
+// compute vertically adjacent tiles, each loads its own A tile and HALF of the shared B tile, and TMA
+// multicast delivers both halves to both CTAs (32 KB instead of 48 KB per CTA per k-block).
 //
 // Operand layouts are described, not materialised: a K-major operand is one TMA box of
 // [rows x 64] bf16 per stage; an MN-major operand (the "transposed" view: token-mixing reads the
@@ -19,6 +25,7 @@
 // need no padding copies of the activations; only rows whose byte pitch is not a multiple of 16 B
 // (token-mix weights) are re-packed by mc_cast_pad.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -28,7 +35,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per k-block = 128 B = one swizzle row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -41,6 +49,7 @@ struct GemmTcArgs {
     int a_mn, b_mn, a_batched, b_batched;
     int BN, stages, stage_bytes, b_tx_bytes;
     int tiles_m, tiles_n, split_k, num_tiles;
+    int cluster, tiles_m_eff, b_box_rows;   // cluster: CTAs per cluster along M (1 or 2)
     // epilogue
     void* C;
     int c_bf16;
@@ -61,10 +70,11 @@ struct TileCoord {
     int tm, tn, b, kb_begin, kb_end;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmTcArgs& g, int t) {
+// t indexes work items of a cluster; the CTA of rank r in the cluster takes m-tile tm_eff * cluster + r
+__device__ __forceinline__ TileCoord decode_tile(const GemmTcArgs& g, int t, int cta_rank) {
     TileCoord c;
-    c.tm = t % g.tiles_m;
-    t /= g.tiles_m;
+    c.tm = (t % g.tiles_m_eff) * g.cluster + cta_rank;
+    t /= g.tiles_m_eff;
     c.tn = t % g.tiles_n;
     t /= g.tiles_n;
     c.b = t % g.out_batch;
@@ -190,6 +200,189 @@ __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], fl
     }
 }
 
+// ---- 256-bit global accesses -------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256f(const float* p, float (&r)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void stg256f(float* p, const float (&r)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]),
+                 "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+enum { EPI_GENERIC = 0, EPI_ACT_FWD = 1, EPI_RESID = 2, EPI_ACT_BWD = 3, EPI_PLAIN = 4 };
+
+// QuickGELU on the tanh unit: x*sigmoid(1.702x) = hx + hx*tanh(0.851x), hx = x/2
+__device__ __forceinline__ float gelu_t(float x) {
+    const float hx = 0.5f * x;
+    return fmaf(hx, tanh_approx(0.851f * x), hx);
+}
+// derivative for the backward epilogues: sigmoid from ex2 + rcp (both ~1 ulp) instead of tanh.approx (2^-11):
+// the error of g'(z) multiplies every gradient that flows through the block
+__device__ __forceinline__ float gelu_grad_t(float z) {
+    float e, s;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * z));   // exp(-1.702 z)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+    const float w = kGeluA * z;
+    return fmaf(fmaf(-w, s, w), s, s);  // s + w*s*(1-s)
+}
+
+// One full 32-column chunk (all columns valid, 32-byte aligned rows), specialised per epilogue kind.
+// Global operands of the chunk (residual / saved pre-activation) are requested BEFORE the TMEM load is
+// waited for, so their latency overlaps it.
+template <int EPI>
+__device__ __forceinline__ void chunk32(const GemmTcArgs& g, uint32_t taddr, float bias_m, long long crow, int b, int n,
+                                        bool ok) {
+    // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane executes it; only the global accesses are
+    // predicated on the row being inside M.
+    uint32_t v[32];
+    if constexpr (EPI == EPI_RESID) {
+        const float* rp = g.R + (long long)b * g.r_bs + crow * g.ldr + n;
+        float r[4][8];
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ldg256f(rp + 8 * j, r[j]);
+        }
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (!ok) return;
+        float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o[8];
+            if (g.bias_mode == MC_BIAS_N) {
+                float bv[8];
+                ldg256f(g.bias + n + 8 * j, bv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]) + bv[i] + r[j][i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]) + bias_m + r[j][i];
+            }
+            stg256f(cp + 8 * j, o);
+        }
+    } else if constexpr (EPI == EPI_ACT_BWD) {
+        const __half* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
+        uint32_t z[2][8];
+        if (ok) {
+            ldg256(zp, z[0]);
+            ldg256(zp + 16, z[1]);
+        }
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (!ok) return;
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 zz = unpack_h2(z[j][i]);
+                const float a = __uint_as_float(v[16 * j + 2 * i]) * gelu_grad_t(zz.x);
+                const float c = __uint_as_float(v[16 * j + 2 * i + 1]) * gelu_grad_t(zz.y);
+                o[i] = pack_bf16x2(a, c);
+            }
+            stg256(cp + 16 * j, o);
+        }
+    } else if constexpr (EPI == EPI_ACT_FWD) {
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (!ok) return;
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        __half* zp = g.zout != nullptr ? g.zout + (long long)b * g.z_bs + crow * g.ldz + n : nullptr;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float x[16];
+            if (g.bias_mode == MC_BIAS_N) {
+                float bv[2][8];
+                ldg256f(g.bias + n + 16 * j, bv[0]);
+                ldg256f(g.bias + n + 16 * j + 8, bv[1]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[16 * j + i]) + bv[i >> 3][i & 7];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[16 * j + i]) + bias_m;
+            }
+            if (zp != nullptr) {
+                uint32_t zo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zo[i] = pack_h2_sat(x[2 * i], x[2 * i + 1]);
+                stg256(zp + 16 * j, zo);
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(gelu_t(x[2 * i]), gelu_t(x[2 * i + 1]));
+            stg256(cp + 16 * j, o);
+        }
+    } else {  // EPI_PLAIN: fp32 store / read-modify-write / atomic add, no bias, no activation
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (!ok) return;
+        float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        if (g.atomic) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                atomicAdd(reinterpret_cast<float4*>(cp + 4 * j),
+                          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]);
+                if (g.accumulate) {
+                    float c0[8];
+                    ldg256f(cp + 8 * j, c0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] += c0[i];
+                }
+                stg256f(cp + 8 * j, o);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs g) {
     extern __shared__ uint8_t dyn_smem[];
@@ -202,6 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+    const int csize = g.cluster;
+    const int cta_rank = csize > 1 ? (int)cluster_ctarank() : 0;
+    const int work0 = blockIdx.x / csize, work_stride = gridDim.x / csize;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -210,11 +406,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), csize);  // released by the MMA warp of every CTA of the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), 4);
+            mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
         }
         fence_mbar_init();
     }
@@ -223,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -231,8 +427,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(g, t);
+            const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
+            for (int t = work0; t < g.num_tiles; t += work_stride) {
+                const TileCoord tc = decode_tile(g, t, cta_rank);
                 const int m0 = tc.tm * BM, n0 = tc.tn * g.BN;
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     int bb = tc.b, kk = kb * BK;
@@ -252,11 +449,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         tma_load_3d(a_dst, &tmA, bar, kk, m0, ba);
                     }
-                    if (g.b_mn) {
-                        for (int j = 0; j * 64 < g.BN; ++j)
-                            tma_load_3d(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt);
+                    if (csize == 1) {
+                        if (g.b_mn) {
+                            for (int j = 0; j * 64 < g.BN; ++j)
+                                tma_load_3d(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt);
+                        } else {
+                            tma_load_3d(b_dst, &tmB, bar, kk, n0, bbt);
+                        }
                     } else {
-                        tma_load_3d(b_dst, &tmB, bar, kk, n0, bbt);
+                        // this CTA fetches its share of the B tile and multicasts it to the whole cluster
+                        if (g.b_mn) {
+                            for (int j = cta_rank; j * 64 < g.BN; j += csize)
+                                tma_load_3d_mc(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt, mc_mask);
+                        } else {
+                            const int r0 = cta_rank * g.b_box_rows;
+                            tma_load_3d_mc(b_dst + r0 * (BK * 2), &tmB, bar, kk, n0 + r0, bbt, mc_mask);
+                        }
                     }
                     if (++stage == (uint32_t)g.stages) {
                         stage = 0;
@@ -273,9 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t b_kstep = g.b_mn ? 2048u : 32u;
             const uint32_t a_lbo = g.a_mn ? kGroupBytes : 16u;
             const uint32_t b_lbo = g.b_mn ? kGroupBytes : 16u;
+            const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(g, t);
+            for (int t = work0; t < g.num_tiles; t += work_stride) {
+                const TileCoord tc = decode_tile(g, t, cta_rank);
                 mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -290,7 +499,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t bd = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024u);
                         umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(smem_u32(&empty_bar[stage]));
+                    // the stage is shared through multicast: release it in every CTA of the cluster
+                    if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
+                    else umma_commit_mc(smem_u32(&empty_bar[stage]), mc_mask);
                     if (++stage == (uint32_t)g.stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -303,10 +514,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;  // TMEM lane quarter == warp id % 4
+        const int e = warp - 4;
+        const int q = e & 3;    // TMEM lane quarter == warp id % 4
+        const int half = e >> 2;  // which 32-column chunks of every 64 this warp drains
         uint32_t as = 0, aphase = 0;
-        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(g, t);
+        for (int t = work0; t < g.num_tiles; t += work_stride) {
+            const TileCoord tc = decode_tile(g, t, cta_rank);
             const int m = tc.tm * BM + q * 32 + lane;
             const int n0 = tc.tn * g.BN;
             const bool row_ok = m < g.M;
@@ -316,21 +529,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
-            for (int c = 0; c < g.BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c, v);
-                tmem_ld_wait();
+            for (int c = half * 32; c < g.BN; c += 64) {
                 const int nb = n0 + c;
-                if (row_ok && nb < g.N) {
-                    const int rem = g.N - nb;
+                if (nb >= g.N) break;  // warp-uniform
+                const int rem = g.N - nb;
+                if (EPI != EPI_GENERIC && rem >= 32) {
+                    chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok);
+                } else {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const int ncols = rem - j8 * 8;
-                        if (ncols > 0) {
-                            float x[8];
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const int ncols = rem - j8 * 8;
+                            if (ncols > 0) {
+                                float x[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j8 * 8 + j]);
-                            epilogue8(g, x, bias_m, crow, tc.b, nb + j8 * 8, ncols, g.vec_ok && ncols >= 8);
+                                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j8 * 8 + j]);
+                                epilogue8(g, x, bias_m, crow, tc.b, nb + j8 * 8, ncols, g.vec_ok && ncols >= 8);
+                            }
                         }
                     }
                 }
@@ -344,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -403,16 +621,50 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int major, int64_t rows,
     return MC_OK;
 }
 
-// Modelled cost (cycles, arbitrary unit) of running the problem with a given BN / split.
-double model_cost(int64_t M, int64_t N, int64_t out_batch, int64_t kb_total, int BN, int split, int sms, int heavy_epi) {
-    const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN) * out_batch * split;
-    const int64_t rounds = ceil_div(tiles, sms);
+// Modelled cost (SM cycles) of running the problem with a given BN / split / cluster size.  A k-block of
+// a 128 x BN tile costs max(tensor time 2*BN, L2->SM operand delivery at ~42 B/clk/SM); tiles are dealt to
+// sms/cluster work slots in rounds (wave quantisation dominates at these sizes).
+double model_cost(int64_t M, int64_t N, int64_t out_batch, int64_t kb_total, int BN, int split, int sms, int heavy_epi,
+                  int cluster) {
+    const int64_t tiles_m_eff = ceil_div(ceil_div(M, BM), cluster);
+    const int64_t work = tiles_m_eff * ceil_div(N, BN) * out_batch * split;
+    const int64_t rounds = ceil_div(work, sms / cluster);
     const double kb = double(kb_total) / split;
-    const double t_mma = 4.0 * (BN / 2.0 > (128 + BN) / 4.0 ? BN / 2.0 : (128 + BN) / 4.0);
-    const double epi = BN * (heavy_epi ? 16.0 : 6.0);
-    double tile = kb * t_mma;
+    const double bytes = (BM + double(BN) / cluster) * BK * 2;
+    const double t_l2 = bytes / 42.0, t_mma = 2.0 * BN;
+    const double epi = BN * (heavy_epi ? 10.0 : 5.0);
+    double tile = kb * (t_mma > t_l2 ? t_mma : t_l2);
     if (epi > tile) tile = epi;  // epilogue of tile i overlaps the MMAs of tile i+1
-    return rounds * (tile + 600.0) + epi + 2500.0;
+    return rounds * (tile + 500.0) + epi + 2500.0;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& g, int grid, size_t smem,
+                cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI>, tmA, tmB, g));
+    return MC_OK;
 }
 
 }  // namespace
@@ -446,31 +698,38 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     const bool linear_epi = p->act == MC_ACT_NONE && p->zout == nullptr && p->R == nullptr &&
                             p->bias_mode == MC_BIAS_NONE && p->c_dtype == MC_F32 && p->accumulate;
     const int heavy = p->act != MC_ACT_NONE;
-    // tile width / split-K selection by a small cost model (wave quantisation dominates at these sizes)
-    int best_bn = 0, best_split = 1;
+    // tile width / split-K / cluster selection by a small cost model
+    const int tiles_m_all = (int)ceil_div(p->M, BM);
+    static const int allow_cluster = env_int("MC_GEMM_CLUSTER", 1);
+    int best_bn = 0, best_split = 1, best_cluster = 1;
     double best = 1e300;
     const int n_cap = (int)(ceil_div(p->N, 32) * 32);
-    for (int bn = 256; bn >= 32; bn -= 32) {
-        if (bn > n_cap && bn != 32) continue;
-        int max_split = 1;
-        if (p->split_k > 1) max_split = (int)p->split_k;
-        else if (p->split_k == 0 && linear_epi) max_split = 64;
-        for (int sp = (p->split_k > 1 ? max_split : 1); sp <= max_split; sp *= 2) {
-            if (sp > g.kb_total) break;
-            double c = model_cost(p->M, p->N, g.out_batch, g.kb_total, bn, sp, sms, heavy);
-            if (sp > 1) c += 800.0;  // atomics
-            if (c < best) { best = c; best_bn = bn; best_split = sp; }
+    for (int cl = 1; cl <= (allow_cluster && tiles_m_all >= 2 ? 2 : 1); ++cl) {
+        for (int bn = 256; bn >= 32; bn -= 32) {
+            if (bn > n_cap && bn != 32) continue;
+            int max_split = 1;
+            if (p->split_k > 1) max_split = (int)p->split_k;
+            else if (p->split_k == 0 && linear_epi) max_split = 64;
+            for (int sp = (p->split_k > 1 ? max_split : 1); sp <= max_split; sp *= 2) {
+                if (sp > g.kb_total) break;
+                double c = model_cost(p->M, p->N, g.out_batch, g.kb_total, bn, sp, sms, heavy, cl);
+                if (sp > 1) c += 800.0;  // atomics
+                if (c < best) { best = c; best_bn = bn; best_split = sp; best_cluster = cl; }
+            }
         }
     }
     MC_CHECK(best_bn > 0, "gemm: no tile configuration");
     if (best_split > 1) MC_CHECK(linear_epi || p->split_k > 1, "gemm: split-K needs a linear fp32 accumulate epilogue");
     g.BN = best_bn;
     g.split_k = best_split;
-    g.tiles_m = (int)ceil_div(p->M, BM);
+    g.cluster = best_cluster;
+    g.tiles_m = tiles_m_all;
+    g.tiles_m_eff = (int)ceil_div(g.tiles_m, g.cluster);
     g.tiles_n = (int)ceil_div(p->N, g.BN);
-    const long long nt = (long long)g.tiles_m * g.tiles_n * g.out_batch * g.split_k;
+    const long long nt = (long long)g.tiles_m_eff * g.tiles_n * g.out_batch * g.split_k;   // work items per cluster
     MC_CHECK(nt < (1ll << 31), "gemm: too many tiles");
     g.num_tiles = (int)nt;
+    g.b_box_rows = g.BN / g.cluster;
     g.b_tx_bytes = g.b_mn ? (int)(ceil_div(g.BN, 64) * kGroupBytes) : g.BN * BK * 2;
     g.stage_bytes = (int)(kABytes + ceil_div(g.b_tx_bytes, 1024) * 1024);
     const int smem_budget = 200 * 1024;
@@ -497,17 +756,30 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     CUtensorMap tmA, tmB;
     int rc = make_operand_map(&tmA, p->A, p->a_major, p->M, p->K, p->lda, p->batch, p->a_batch_stride, BM, "A");
     if (rc != MC_OK) return rc;
-    rc = make_operand_map(&tmB, p->B, p->b_major, p->N, p->K, p->ldb, p->batch, p->b_batch_stride, g.BN, "B");
+    rc = make_operand_map(&tmB, p->B, p->b_major, p->N, p->K, p->ldb, p->batch, p->b_batch_stride, g.b_box_rows, "B");
     if (rc != MC_OK) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_set = true;
-    }
-    const int grid = g.num_tiles < sms ? g.num_tiles : sms;
+    const int slots = sms / g.cluster;
+    const int grid = (g.num_tiles < slots ? g.num_tiles : slots) * g.cluster;
     const size_t smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-    gemm_tc_kernel<<<grid, kThreads, smem_req, stream>>>(tmA, tmB, g);
-    MC_CUDA(cudaGetLastError());
-    return MC_OK;
+    // epilogue specialisation (vector paths need 32-byte aligned rows; anything else takes the generic path)
+    int epi = EPI_GENERIC;
+    if (g.vec_ok && p->row_remap >= 0) {
+        if (p->act == MC_ACT_GELU && g.c_bf16 && p->R == nullptr && !p->accumulate && !g.atomic) epi = EPI_ACT_FWD;
+        else if (p->act == MC_ACT_GELU_BWD && g.c_bf16 && p->R == nullptr && p->zout == nullptr &&
+                 p->bias_mode == MC_BIAS_NONE && !p->accumulate && !g.atomic) epi = EPI_ACT_BWD;
+        else if (p->act == MC_ACT_NONE && !g.c_bf16 && p->R != nullptr && p->zout == nullptr && !p->accumulate &&
+                 !g.atomic) epi = EPI_RESID;
+        else if (p->act == MC_ACT_NONE && !g.c_bf16 && p->R == nullptr && p->zout == nullptr &&
+                 p->bias_mode == MC_BIAS_NONE) epi = EPI_PLAIN;
+    }
+    static const int force_generic = env_int("MC_GEMM_GENERIC_EPI", 0);
+    if (force_generic) epi = EPI_GENERIC;
+    switch (epi) {
+        case EPI_ACT_FWD: return launch_gemm<EPI_ACT_FWD>(tmA, tmB, g, grid, smem_req, stream);
+        case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, g, grid, smem_req, stream);
+        case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, g, grid, smem_req, stream);
+        case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, g, grid, smem_req, stream);
+        default: return launch_gemm<EPI_GENERIC>(tmA, tmB, g, grid, smem_req, stream);
+    }
 }

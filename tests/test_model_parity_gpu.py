@@ -191,12 +191,12 @@ def test_cpu_tensors_and_bad_config_raise():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_b32_full_size_vs_oracle(precision):
-    """BASELINE.json configs[1] architecture (Mixer-CLIP B/32-size, 12+12 layers, 111M parameters) at batch 8
+    """BASELINE.json configs[1] architecture (Mixer-CLIP B/32-size, 12+12 layers, 111M parameters) at batch 16
     against the fp64 oracle run on the host: north_star's tolerances on embeddings, logits, loss, gradients."""
     from oracle import mixer_clip_oracle as O
     cfg = O.CONFIGS["B32"]
     sd = O.seeded_state_dict(cfg, seed=0)
-    image, text = O.synthetic_batch(cfg, 8, seed=1)
+    image, text = O.synthetic_batch(cfg, 16, seed=1)
     torch.set_num_threads(os.cpu_count())
     truth = O.loss_and_grads({k: v.double() for k, v in sd.items()}, image.double(), text)
     model = _build(cfg, sd, precision)
