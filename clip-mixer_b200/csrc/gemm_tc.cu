@@ -26,6 +26,7 @@
 // (token-mix weights) are re-packed by mc_cast_pad.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -50,6 +51,9 @@ struct GemmTcArgs {
     int BN, stages, stage_bytes, b_tx_bytes;
     int tiles_m, tiles_n, split_k, num_tiles;
     int cluster, tiles_m_eff, b_box_rows;   // cluster: CTAs per cluster along M (1 or 2)
+    int tma_epi;                            // outputs leave through smem staging + TMA store
+    int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
+    int epi_smem_off;                       // byte offset of the epilogue staging area from tiles_base
     // epilogue
     void* C;
     int c_bf16;
@@ -360,6 +364,137 @@ __device__ __forceinline__ void chunk32(const GemmTcArgs& g, uint32_t taddr, flo
     }
 }
 
+// ---- TMA store side ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C chunk (2 KB) + an fp16 Z chunk (2 KB)
+
+// One 32-column chunk leaving through shared memory and a TMA store: every lane owns one output row, writes it
+// into a swizzled staging tile (conflict-free 16-byte stores), and one lane hands the [32 x 32] box to the TMA
+// unit, which writes full lines to L2 and clips rows >= M / columns >= N by itself.  Compared with per-lane
+// global stores (one 32-byte sector per lane = 32 L1 wavefronts per instruction) this removes ~90 % of the
+// epilogue's L1 traffic, which ncu showed to be what kept the tensor pipe at 48 % (profiles/r1b_*).
+template <int EPI>
+__device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
+                                               uint32_t taddr, uint32_t stage, float bias_m, bool row_ok, long long crow,
+                                               int m_base, int b, int n, int lane) {
+    uint32_t v[32];
+    const bool full = n + 32 <= g.N;
+    if constexpr (EPI == EPI_ACT_BWD) {
+        // saved pre-activation of this row (fp16): direct 256-bit loads, requested before the TMEM load is waited for
+        uint32_t z[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[j][i] = 0u;
+        const __half* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
+        if (row_ok) {
+            if (full && g.vec_ok) {
+                ldg256(zp, z[0]);
+                ldg256(zp + 16, z[1]);
+            } else {
+                const unsigned short* zs = reinterpret_cast<const unsigned short*>(zp);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t h = (n + i < g.N) ? (uint32_t)zs[i] : 0u;
+                    z[i >> 4][(i & 15) >> 1] |= h << ((i & 1) * 16);
+                }
+            }
+        }
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 zz = unpack_h2(z[i >> 3][i & 7]);
+            o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * gelu_grad_t(zz.x), __uint_as_float(v[2 * i + 1]) * gelu_grad_t(zz.y));
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(tmC, stage, n, m_base, b);
+            bulk_commit();
+        }
+    } else if constexpr (EPI == EPI_ACT_FWD) {
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        float x[32];
+        if (g.bias_mode == MC_BIAS_N) {
+            if (full && g.vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float bv[8];
+                    ldg256f(g.bias + n + 8 * j, bv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[8 * j + i] = __uint_as_float(v[8 * j + i]) + bv[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + (n + i < g.N ? g.bias[n + i] : 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + bias_m;
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+        if (g.zout != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                sts128(rowp + 2048 + ((j ^ sw) << 4), pack_h2_sat(x[8 * j], x[8 * j + 1]), pack_h2_sat(x[8 * j + 2], x[8 * j + 3]),
+                       pack_h2_sat(x[8 * j + 4], x[8 * j + 5]), pack_h2_sat(x[8 * j + 6], x[8 * j + 7]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            sts128(rowp + ((j ^ sw) << 4), pack_bf16x2(gelu_t(x[8 * j]), gelu_t(x[8 * j + 1])),
+                   pack_bf16x2(gelu_t(x[8 * j + 2]), gelu_t(x[8 * j + 3])), pack_bf16x2(gelu_t(x[8 * j + 4]), gelu_t(x[8 * j + 5])),
+                   pack_bf16x2(gelu_t(x[8 * j + 6]), gelu_t(x[8 * j + 7])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(tmC, stage, n, m_base, b);
+            if (g.zout != nullptr) tma_store_3d(tmZ, stage + 2048, n, m_base, b);
+            bulk_commit();
+        }
+    } else {  // EPI_PLAIN: fp32 tile, plain store or reduce-add (accumulate / split-K)
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint32_t rowp = stage + lane * 128, sw = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(rowp + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if (g.accumulate || g.atomic) tma_reduce_add_3d(tmC, stage, n, m_base, b);
+            else tma_store_3d(tmC, stage, n, m_base, b);
+            bulk_commit();
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -382,9 +517,49 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
                  : "memory");
 }
 
-template <int EPI>
+// ---- cta_group::2 (CTA pair) primitives -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int EPI, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTcArgs g) {
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -398,25 +573,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int csize = g.cluster;
     const int cta_rank = csize > 1 ? (int)cluster_ctarank() : 0;
     const int work0 = blockIdx.x / csize, work_stride = gridDim.x / csize;
+    // cta_group::2 pair mode is a separate instantiation: a kernel that contains pair instructions can only be
+    // launched with an even cluster size
+    constexpr bool two = TWO;              // rank 0 is the leader and issues every MMA
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (g.tma_epi) {
+            tma_prefetch_desc(&tmC);
+            if (g.zout != nullptr) tma_prefetch_desc(&tmZ);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), csize);  // released by the MMA warp of every CTA of the cluster
+            // multicast mode: released by the MMA warp of every CTA of the cluster; pair mode: one multicast
+            // commit of the leader's MMA thread reaches both CTAs
+            mbar_init(smem_u32(&empty_bar[s]), two ? 1 : csize);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+            // pair mode: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
+            mbar_init(smem_u32(&tempty_bar[s]), two ? 2 * kEpiWarps : kEpiWarps);
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
-        tmem_relinquish();
+        if constexpr (TWO) {
+            tmem_alloc_2cta(smem_u32(&tmem_base_smem), kTmemCols);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -441,8 +632,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t bar = smem_u32(&full_bar[stage]);
                     const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
                     const uint32_t b_dst = a_dst + kABytes;
-                    mbar_arrive_expect_tx(bar, kABytes + g.b_tx_bytes);
                     const int ba = g.a_batched ? bb : 0, bbt = g.b_batched ? bb : 0;
+                    if constexpr (TWO) {
+                        // pair mode: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                        const uint32_t lbar = leader ? bar : mapa_u32(bar, 0);
+                        if (leader) mbar_arrive_expect_tx(bar, 2u * (kABytes + g.b_tx_bytes));
+                        if (g.a_mn) {
+                            tma_load_3d_2sm(a_dst, &tmA, lbar, m0, kk, ba);
+                            tma_load_3d_2sm(a_dst + kGroupBytes, &tmA, lbar, m0 + 64, kk, ba);
+                        } else {
+                            tma_load_3d_2sm(a_dst, &tmA, lbar, kk, m0, ba);
+                        }
+                        const int nh = n0 + cta_rank * (g.BN / 2);   // this CTA supplies half of the B tile's columns
+                        if (g.b_mn) {
+                            for (int j = 0; j * 64 < g.BN / 2; ++j)
+                                tma_load_3d_2sm(b_dst + j * kGroupBytes, &tmB, lbar, nh + j * 64, kk, bbt);
+                        } else {
+                            tma_load_3d_2sm(b_dst, &tmB, lbar, kk, nh, bbt);
+                        }
+                        if (++stage == (uint32_t)g.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(bar, kABytes + g.b_tx_bytes);
                     if (g.a_mn) {
                         tma_load_3d(a_dst, &tmA, bar, m0, kk, ba);
                         tma_load_3d(a_dst + kGroupBytes, &tmA, bar, m0 + 64, kk, ba);
@@ -475,8 +689,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, g.BN, g.a_mn, g.b_mn);
+        if (lane == 0 && (!two || leader)) {
+            const uint32_t idesc = make_idesc_bf16(two ? 2 * BM : BM, g.BN, g.a_mn, g.b_mn);
             const uint32_t a_kstep = g.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
             const uint32_t b_kstep = g.b_mn ? 2048u : 32u;
             const uint32_t a_lbo = g.a_mn ? kGroupBytes : 16u;
@@ -497,17 +711,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024u);
                         const uint64_t bd = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024u);
-                        umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        if constexpr (TWO) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        else umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
                     }
-                    // the stage is shared through multicast: release it in every CTA of the cluster
-                    if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
+                    // the stage is shared through multicast / the pair: release it in every CTA of the cluster
+                    if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&empty_bar[stage]), mc_mask);
+                    else if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
                     else umma_commit_mc(smem_u32(&empty_bar[stage]), mc_mask);
                     if (++stage == (uint32_t)g.stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(smem_u32(&tfull_bar[as]));
+                if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&tfull_bar[as]), mc_mask);
+                else umma_commit(smem_u32(&tfull_bar[as]));
                 as ^= 1u;
                 if (as == 0) aphase ^= 1u;
             }
@@ -529,11 +746,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
+            const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
             for (int c = half * 32; c < g.BN; c += 64) {
                 const int nb = n0 + c;
                 if (nb >= g.N) break;  // warp-uniform
                 const int rem = g.N - nb;
-                if (EPI != EPI_GENERIC && rem >= 32) {
+                if ((EPI == EPI_ACT_FWD || EPI == EPI_ACT_BWD || EPI == EPI_PLAIN) && g.tma_epi) {
+                    chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
+                                        nb, lane);
+                } else if (EPI != EPI_GENERIC && rem >= 32) {
                     chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok);
                 } else {
                     uint32_t v[32];
@@ -555,15 +776,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+            if (lane == 0) {
+                if (two && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+                else mbar_arrive(smem_u32(&tempty_bar[as]));
+            }
             as ^= 1u;
             if (as == 0) aphase ^= 1u;
         }
+        if (g.tma_epi && lane == 0) bulk_wait_all();  // the staging tiles must outlive their TMA stores
     }
 
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------
@@ -631,8 +859,8 @@ double model_cost(int64_t M, int64_t N, int64_t out_batch, int64_t kb_total, int
     const int64_t rounds = ceil_div(work, sms / cluster);
     const double kb = double(kb_total) / split;
     const double bytes = (BM + double(BN) / cluster) * BK * 2;
-    const double t_l2 = bytes / 42.0, t_mma = 2.0 * BN;
-    const double epi = BN * (heavy_epi ? 10.0 : 5.0);
+    const double t_l2 = bytes / 38.0, t_mma = 2.0 * BN;   // L2->SM delivery ~36-40 B/clk/SM (profiles/r1c sweep)
+    const double epi = BN * (heavy_epi ? 14.0 : 6.0);
     double tile = kb * (t_mma > t_l2 ? t_mma : t_l2);
     if (epi > tile) tile = epi;  // epilogue of tile i overlaps the MMAs of tile i+1
     return rounds * (tile + 500.0) + epi + 2500.0;
@@ -643,12 +871,28 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int EPI>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& g, int grid, size_t smem,
-                cudaStream_t stream) {
+// output tensor [batch][rows][cols] (cols contiguous) as a TMA store target with a [32 x 32] box
+int make_store_map(CUtensorMap* map, void* ptr, CUtensorMapDataType dt, int esz, int64_t cols, int64_t rows, int64_t batch,
+                   int64_t ld, int64_t batch_stride, const char* name) {
+    EncodeTiledFn enc = get_encode_fn();
+    MC_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    const bool batched = batch_stride != 0 && batch > 1;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, batched ? (cuuint64_t)batch : 1};
+    cuuint64_t gstride[2] = {(cuuint64_t)ld * esz, batched ? (cuuint64_t)batch_stride * esz : (cuuint64_t)ld * esz * rows};
+    cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    CUresult r = enc(map, dt, 3, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with %d", name, (int)r);
+    return MC_OK;
+}
+
+template <int EPI, bool TWO>
+int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmZ,
+                const GemmTcArgs& g, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -663,8 +907,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI>, tmA, tmB, g));
+    MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, TWO>, tmA, tmB, tmC, tmZ, g));
     return MC_OK;
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmZ,
+                const GemmTcArgs& g, int grid, size_t smem, cudaStream_t stream) {
+    return g.two_cta ? launch_gemm_t<EPI, true>(tmA, tmB, tmC, tmZ, g, grid, smem, stream)
+                     : launch_gemm_t<EPI, false>(tmA, tmB, tmC, tmZ, g, grid, smem, stream);
 }
 
 }  // namespace
@@ -701,12 +952,14 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     // tile width / split-K / cluster selection by a small cost model
     const int tiles_m_all = (int)ceil_div(p->M, BM);
     static const int allow_cluster = env_int("MC_GEMM_CLUSTER", 1);
+    static const int allow_2cta_sel = env_int("MC_GEMM_2CTA", 1);
     int best_bn = 0, best_split = 1, best_cluster = 1;
     double best = 1e300;
     const int n_cap = (int)(ceil_div(p->N, 32) * 32);
     for (int cl = 1; cl <= (allow_cluster && tiles_m_all >= 2 ? 2 : 1); ++cl) {
         for (int bn = 256; bn >= 32; bn -= 32) {
             if (bn > n_cap && bn != 32) continue;
+            if (cl == 2 && g.b_mn && bn % 128 != 0 && allow_2cta_sel) continue;   // pair mode needs whole 64-column groups per CTA
             int max_split = 1;
             if (p->split_k > 1) max_split = (int)p->split_k;
             else if (p->split_k == 0 && linear_epi) max_split = 64;
@@ -717,6 +970,13 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
                 if (c < best) { best = c; best_bn = bn; best_split = sp; best_cluster = cl; }
             }
         }
+    }
+    // tuning / debugging overrides (read on every call; used by tools/gemm_bench.py sweeps)
+    {
+        const int f_bn = env_int("MC_GEMM_BN", 0), f_sp = env_int("MC_GEMM_SPLIT", 0), f_cl = env_int("MC_GEMM_CL", 0);
+        if (f_bn > 0 && f_bn <= 256 && f_bn % 32 == 0) best_bn = f_bn;
+        if (f_sp > 0 && (f_sp == 1 || linear_epi) && f_sp <= g.kb_total) best_split = f_sp;
+        if (f_cl == 1 || (f_cl == 2 && tiles_m_all >= 2)) best_cluster = f_cl;
     }
     MC_CHECK(best_bn > 0, "gemm: no tile configuration");
     if (best_split > 1) MC_CHECK(linear_epi || p->split_k > 1, "gemm: split-K needs a linear fp32 accumulate epilogue");
@@ -729,15 +989,41 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     const long long nt = (long long)g.tiles_m_eff * g.tiles_n * g.out_batch * g.split_k;   // work items per cluster
     MC_CHECK(nt < (1ll << 31), "gemm: too many tiles");
     g.num_tiles = (int)nt;
+    static const int allow_2cta = env_int("MC_GEMM_2CTA", 1);
+    g.two_cta = (allow_2cta && g.cluster == 2 && g.BN % 32 == 0 && (!g.b_mn || g.BN % 128 == 0)) ? 1 : 0;
     g.b_box_rows = g.BN / g.cluster;
-    g.b_tx_bytes = g.b_mn ? (int)(ceil_div(g.BN, 64) * kGroupBytes) : g.BN * BK * 2;
+    // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
+    const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;
+    g.b_tx_bytes = g.b_mn ? (int)(ceil_div(bn_cta, 64) * kGroupBytes) : bn_cta * BK * 2;
     g.stage_bytes = (int)(kABytes + ceil_div(g.b_tx_bytes, 1024) * 1024);
-    const int smem_budget = 200 * 1024;
+    // epilogue kind: decided before the smem split because the TMA-store epilogues need a staging area
+    const bool c_bf16 = p->c_dtype == MC_BF16;
+    const bool atomic = best_split > 1;
+    int epi = EPI_GENERIC;
+    if (p->act == MC_ACT_GELU && c_bf16 && p->R == nullptr && !p->accumulate && !atomic) epi = EPI_ACT_FWD;
+    else if (p->act == MC_ACT_GELU_BWD && c_bf16 && p->R == nullptr && p->zout == nullptr &&
+             p->bias_mode == MC_BIAS_NONE && !p->accumulate && !atomic) epi = EPI_ACT_BWD;
+    else if (p->act == MC_ACT_NONE && !c_bf16 && p->R != nullptr && p->zout == nullptr && !p->accumulate && !atomic)
+        epi = EPI_RESID;
+    else if (p->act == MC_ACT_NONE && !c_bf16 && p->R == nullptr && p->zout == nullptr && p->bias_mode == MC_BIAS_NONE)
+        epi = EPI_PLAIN;
+    static const int force_generic = env_int("MC_GEMM_GENERIC_EPI", 0);
+    static const int allow_tma_epi = env_int("MC_GEMM_TMA_EPI", 1);
+    if (force_generic) epi = EPI_GENERIC;
+    // TMA stores need 16-byte aligned bases / pitches and no row remapping
+    auto al16 = [](const void* q, long long ld, long long bs, int esz) {
+        return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 16 == 0) && (ld * esz) % 16 == 0 && (bs * esz) % 16 == 0);
+    };
+    g.tma_epi = allow_tma_epi && (epi == EPI_ACT_FWD || epi == EPI_ACT_BWD || epi == EPI_PLAIN) && p->row_remap == 0 &&
+                al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2);
+    const int epi_bytes = g.tma_epi ? kEpiWarps * (int)kEpiWarpBytes : 0;
+    const int smem_budget = 225 * 1024 - epi_bytes;
     g.stages = smem_budget / g.stage_bytes;
     if (g.stages > kMaxStages) g.stages = kMaxStages;
     MC_CHECK(g.stages >= 2, "gemm: not enough shared memory for 2 stages");
-    // Always request >= 114 KB so that at most one CTA is resident per SM (each allocates all of TMEM).
-    const size_t smem = (size_t)g.stages * g.stage_bytes + 1024;
+    g.epi_smem_off = g.stages * g.stage_bytes;
+    // Always request >= 120 KB so that at most one CTA is resident per SM (each allocates all of TMEM).
+    const size_t smem = (size_t)g.stages * g.stage_bytes + epi_bytes + 1024;
 
     g.C = p->C; g.c_bf16 = p->c_dtype == MC_BF16; g.ldc = p->ldc; g.c_bs = p->c_batch_stride;
     g.accumulate = p->accumulate; g.atomic = g.split_k > 1; g.row_remap = p->row_remap;
@@ -759,27 +1045,36 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     rc = make_operand_map(&tmB, p->B, p->b_major, p->N, p->K, p->ldb, p->batch, p->b_batch_stride, g.b_box_rows, "B");
     if (rc != MC_OK) return rc;
 
+    CUtensorMap tmC, tmZ;
+    memset(&tmC, 0, sizeof(tmC));
+    memset(&tmZ, 0, sizeof(tmZ));
+    if (g.tma_epi) {
+        const int esz = c_bf16 ? 2 : 4;
+        rc = make_store_map(&tmC, p->C, c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, esz, p->N,
+                            p->M, g.out_batch, p->ldc, p->c_batch_stride, "C");
+        if (rc != MC_OK) return rc;
+        if (p->zout != nullptr) {
+            rc = make_store_map(&tmZ, p->zout, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->N, p->M, g.out_batch, p->ldz,
+                                p->z_batch_stride, "Z");
+            if (rc != MC_OK) return rc;
+        }
+    }
+    // the direct (non-TMA) specialised paths use 256-bit accesses and need 32-byte aligned rows
+    if (!g.tma_epi && epi != EPI_GENERIC && !(g.vec_ok && p->row_remap >= 0)) epi = EPI_GENERIC;
+
     const int slots = sms / g.cluster;
     const int grid = (g.num_tiles < slots ? g.num_tiles : slots) * g.cluster;
+    static const int debug = env_int("MC_GEMM_DEBUG", 0);
+    if (debug)
+        fprintf(stderr, "[gemm_tc] M=%d N=%d K=%d batch=%d kspan=%d a%db%d -> BN=%d split=%d cluster=%d 2cta=%d stages=%d epi=%d tma_epi=%d tiles=%d grid=%d\n",
+                g.M, g.N, g.K, (int)p->batch, g.k_spans_batch, g.a_mn, g.b_mn, g.BN, g.split_k, g.cluster, g.two_cta, g.stages, epi,
+                g.tma_epi, g.num_tiles, grid);
     const size_t smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-    // epilogue specialisation (vector paths need 32-byte aligned rows; anything else takes the generic path)
-    int epi = EPI_GENERIC;
-    if (g.vec_ok && p->row_remap >= 0) {
-        if (p->act == MC_ACT_GELU && g.c_bf16 && p->R == nullptr && !p->accumulate && !g.atomic) epi = EPI_ACT_FWD;
-        else if (p->act == MC_ACT_GELU_BWD && g.c_bf16 && p->R == nullptr && p->zout == nullptr &&
-                 p->bias_mode == MC_BIAS_NONE && !p->accumulate && !g.atomic) epi = EPI_ACT_BWD;
-        else if (p->act == MC_ACT_NONE && !g.c_bf16 && p->R != nullptr && p->zout == nullptr && !p->accumulate &&
-                 !g.atomic) epi = EPI_RESID;
-        else if (p->act == MC_ACT_NONE && !g.c_bf16 && p->R == nullptr && p->zout == nullptr &&
-                 p->bias_mode == MC_BIAS_NONE) epi = EPI_PLAIN;
-    }
-    static const int force_generic = env_int("MC_GEMM_GENERIC_EPI", 0);
-    if (force_generic) epi = EPI_GENERIC;
     switch (epi) {
-        case EPI_ACT_FWD: return launch_gemm<EPI_ACT_FWD>(tmA, tmB, g, grid, smem_req, stream);
-        case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, g, grid, smem_req, stream);
-        case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, g, grid, smem_req, stream);
-        case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, g, grid, smem_req, stream);
-        default: return launch_gemm<EPI_GENERIC>(tmA, tmB, g, grid, smem_req, stream);
+        case EPI_ACT_FWD: return launch_gemm<EPI_ACT_FWD>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        default: return launch_gemm<EPI_GENERIC>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
     }
 }
