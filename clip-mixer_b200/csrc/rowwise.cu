@@ -180,6 +180,112 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm backward, dense case (the 48 block-level calls of a step), split in two HBM-bound kernels:
+//   rows: dx = dres + LNbwd(dy)  (+ act copy, + row sums) - no cross-row accumulators, so few registers and
+//         full occupancy;
+//   cols: dgamma, dbeta, column sums of dx - threads own columns, loop over rows (operands just written by
+//         the row kernel are mostly L2-resident).
+// The fused kernel above keeps serving the gather / class-token variants (3 calls per step).
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+                   float* __restrict__ dx, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
+                   long long rowsum_period, long long rows, int D) {
+    const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + row * (long long)D;
+    const float* dyr = dy + row * (long long)D;
+    float4 xh[VPL], d[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+            const float4 xv = ld4(xr + c), g = ld4(dyr + c), gm = ld4(gamma + c);
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            d[i] = make_float4(g.x * gm.x, g.y * gm.y, g.z * gm.z, g.w * gm.w);
+            s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+            s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
+        } else {
+            xh[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float invD = 1.0f / D;
+    const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
+    float rsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+            float4 o;
+            o.x = rs * (d[i].x - c1 - xh[i].x * c2);
+            o.y = rs * (d[i].y - c1 - xh[i].y * c2);
+            o.z = rs * (d[i].z - c1 - xh[i].z * c2);
+            o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+            if (dres != nullptr) {
+                const float4 r = ld4(dres + row * (long long)D + c);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            st4(dx + row * (long long)D + c, o);
+            if (dx_act != nullptr) st_act4(dx_act, act_dtype, row * (long long)D + c, o);
+            rsum += o.x + o.y + o.z + o.w;
+        }
+    }
+    if (rowsum_out != nullptr) {
+        rsum = warp_sum(rsum);
+        if (lane == 0) atomicAdd(rowsum_out + row % rowsum_period, rsum);
+    }
+}
+
+// block: 64 column groups (float4) x 4 row lanes; grid (ceil(D/256), row chunks)
+__global__ void __launch_bounds__(256)
+ln_bwd_cols_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ dx, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, float* __restrict__ colsum_out, long long rows, int D,
+                   long long rows_per_block) {
+    __shared__ float4 red[3][4][64];
+    const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    const int c = (blockIdx.x * 64 + cg) * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
+    if (c < D) {
+#pragma unroll 4
+        for (long long r = r0 + rl; r < r1; r += 4) {
+            const float4 g = ld4(dy + r * D + c), xv = ld4(x + r * D + c);
+            const float mu = mean[r], rs = rstd[r];
+            ag.x += g.x * (xv.x - mu) * rs; ag.y += g.y * (xv.y - mu) * rs;
+            ag.z += g.z * (xv.z - mu) * rs; ag.w += g.w * (xv.w - mu) * rs;
+            ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+            if (colsum_out != nullptr) {
+                const float4 o = ld4(dx + r * D + c);
+                ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+            }
+        }
+    }
+    red[0][rl][cg] = ag; red[1][rl][cg] = ab; red[2][rl][cg] = ac;
+    __syncthreads();
+    if (rl == 0 && c < D) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            float* out = w == 0 ? dgamma : w == 1 ? dbeta : colsum_out;
+            if (out == nullptr) continue;
+            float4 a = red[w][0][cg];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const float4 b = red[w][k][cg];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            atomicAdd(reinterpret_cast<float4*>(out + c), a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bias-gradient reductions
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -189,7 +295,56 @@ __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// out[c] += sum_r x[r,c]; block = 128 threads x 2 columns, grid.y splits the rows
+// 8 consecutive values of an act tensor as floats (16-byte load for bf16, 2 x 16-byte for fp32)
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = ld4(p), b = ld4(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
+}
+
+// out[c] += sum_r x[r,c]: block = 32 column groups of 8 x 8 row lanes; grid (ceil(cols/256), row chunks).
+// Requires cols % 8 == 0 and 16-byte aligned rows (host checks, else the scalar kernel below runs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, float* __restrict__ out,
+                  long long rows_per_block) {
+    __shared__ float red[8][32][9];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const long long c = ((long long)blockIdx.x * 32 + cg) * 8;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {
+#pragma unroll 4
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            float v[8];
+            load8<T>(x + r * ld + c, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][cg][i] = acc[i];
+    __syncthreads();
+    // 256 threads -> 256 columns of the block
+    const int col = threadIdx.x;
+    const long long gc = (long long)blockIdx.x * 256 + col;
+    if (gc < cols) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[k][col >> 3][col & 7];
+        atomicAdd(out + gc, sum);
+    }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, float* __restrict__ out,
                               long long rows_per_block) {
@@ -208,16 +363,24 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, long long
     if (two) atomicAdd(out + c + 1, s1);
 }
 
-// out[r % period] += sum_c x[r,c]; one warp per row
+// out[r % period] += sum_c x[r,c]; one warp per row, 16-byte loads when the row allows it
 template <typename T>
 __global__ void rowsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, long long period,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, int vec) {
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const T* p = x + row * ld;
     float s = 0.f;
-    for (long long c = lane; c < cols; c += 32) s += to_f<T>(p[c]);
+    if (vec) {
+        for (long long c = lane * 8; c < cols; c += 256) {
+            float v[8];
+            load8<T>(p + c, v);
+            s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+    } else {
+        for (long long c = lane; c < cols; c += 32) s += to_f<T>(p[c]);
+    }
     s = warp_sum(s);
     if (lane == 0) atomicAdd(out + row % period, s);
 }
@@ -238,25 +401,33 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, l
 __constant__ float kImgMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};  // training.py:115
 __constant__ float kImgStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
+// one thread = 4 consecutive pixels of a patch row (patch % 4 == 0): 4-byte (uint8) or 16-byte (fp32) load,
+// 8-byte (bf16) or 16-byte (fp32) store, both coalesced
 template <bool U8>
 __global__ void im2col_kernel(const void* __restrict__ image, long long B, int R, int patch, void* __restrict__ out,
                               int out_dtype) {
     const int g = R / patch;
     const long long Kc = 3ll * patch * patch;
-    const long long total = B * g * g * Kc;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const long long total4 = B * g * g * Kc / 4;
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const long long i = i4 * 4;
     const long long row = i / Kc;
     const int col = (int)(i % Kc);
     const int px = col % patch, py = (col / patch) % patch, c = col / (patch * patch);
     const int gx = (int)(row % g), gy = (int)((row / g) % g);
     const long long b = row / (g * g);
     const long long src = ((b * 3 + c) * R + (gy * patch + py)) * (long long)R + gx * patch + px;
-    float v;
-    if (U8) v = (reinterpret_cast<const uint8_t*>(image)[src] * (1.0f / 255.0f) - kImgMean[c]) / kImgStd[c];
-    else v = reinterpret_cast<const float*>(image)[src];
-    if (out_dtype == MC_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(out)[i] = v;
+    float4 v;
+    if (U8) {
+        const uchar4 u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(image) + src);
+        const float m = kImgMean[c], is = 1.0f / kImgStd[c];
+        v = make_float4((u.x * (1.0f / 255.0f) - m) * is, (u.y * (1.0f / 255.0f) - m) * is,
+                        (u.z * (1.0f / 255.0f) - m) * is, (u.w * (1.0f / 255.0f) - m) * is);
+    } else {
+        v = ld4(reinterpret_cast<const float*>(image) + src);
+    }
+    st_act4(out, out_dtype, i, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +618,24 @@ extern "C" int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, 
     MC_CHECK(rowsum_out == nullptr || rowsum_period > 0, "ln_bwd: rowsum_period must be positive");
     MC_CHECK(cls == nullptr || cls_period > 0, "ln_bwd: cls_period must be positive");
     MC_CHECK(!(dcls != nullptr && colsum_out != nullptr), "ln_bwd: dcls and colsum_out are mutually exclusive");
+    // dense block-level case: row kernel + column kernel (see ln_bwd_rows_kernel)
+    const bool dense = row_index == nullptr && cls == nullptr && dcls == nullptr && dx != nullptr && x_row_stride == D &&
+                       dx_row_stride == D && D % 4 == 0 && aligned16(dgamma) && aligned16(dbeta) && aligned16(colsum_out);
+    if (dense) {
+        const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
+        MC_DISPATCH_VPL(vpl, (ln_bwd_rows_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+                                 dy, x, mean, rstd, gamma, dres, dx, dx_act, act_dtype, rowsum_out, rowsum_period, rows, (int)D)));
+        MC_CUDA(cudaGetLastError());
+        const int64_t col_blocks = ceil_div(D, 256);
+        int64_t row_blocks = ceil_div((int64_t)sm_count() * 3, col_blocks);
+        if (row_blocks > ceil_div(rows, 16)) row_blocks = ceil_div(rows, 16);
+        if (row_blocks < 1) row_blocks = 1;
+        const int64_t rpb = ceil_div(ceil_div(rows, row_blocks), 4) * 4;
+        dim3 g2((unsigned)col_blocks, (unsigned)ceil_div(rows, rpb));
+        ln_bwd_cols_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, dx, dgamma, dbeta, colsum_out, rows, (int)D, rpb);
+        MC_CUDA(cudaGetLastError());
+        return MC_OK;
+    }
     int64_t blocks = ceil_div(rows, kWarpsPerBlock);
     const int64_t cap = (int64_t)sm_count() * 2;
     if (blocks > cap) blocks = cap;
@@ -460,16 +649,25 @@ extern "C" int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, 
 extern "C" int mc_colsum(const void* x, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (rows == 0 || cols == 0) return MC_OK;
+    const int esz = dtype == MC_BF16 ? 2 : 4;
+    const bool vec = cols % 8 == 0 && (ld * esz) % 16 == 0 && aligned16(x);
     const int64_t col_blocks = ceil_div(cols, 256);
     int64_t row_blocks = ceil_div((int64_t)sm_count() * 4, col_blocks);
     if (row_blocks > ceil_div(rows, 64)) row_blocks = ceil_div(rows, 64);
     if (row_blocks < 1) row_blocks = 1;
-    const int64_t rpb = ceil_div(rows, row_blocks);
+    const int64_t rpb = ceil_div(ceil_div(rows, row_blocks), 8) * 8;
     dim3 grid((unsigned)col_blocks, (unsigned)ceil_div(rows, rpb));
-    if (dtype == MC_BF16)
-        colsum_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
-    else
-        colsum_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
+    if (vec) {
+        if (dtype == MC_BF16)
+            colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
+        else
+            colsum_vec_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
+    } else {
+        if (dtype == MC_BF16)
+            colsum_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
+        else
+            colsum_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
+    }
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -480,10 +678,12 @@ extern "C" int mc_rowsum(const void* x, int32_t dtype, int64_t rows, int64_t col
     if (rows == 0 || cols == 0) return MC_OK;
     MC_CHECK(period > 0, "rowsum: period must be positive");
     const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
+    const int esz = dtype == MC_BF16 ? 2 : 4;
+    const int vec = (cols % 8 == 0 && (ld * esz) % 16 == 0 && aligned16(x)) ? 1 : 0;
     if (dtype == MC_BF16)
-        rowsum_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, period, out);
+        rowsum_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, period, out, vec);
     else
-        rowsum_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, period, out);
+        rowsum_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, period, out, vec);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -504,7 +704,9 @@ extern "C" int mc_im2col(const void* image, int32_t image_is_u8, int64_t B, int6
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return MC_OK;
     MC_CHECK(patch > 0 && R % patch == 0, "im2col: resolution %lld not divisible by patch %lld", (long long)R, (long long)patch);
-    const int64_t total = B * 3 * R * R;
+    MC_CHECK(patch % 4 == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "im2col: patch size must be a multiple of 4 and buffers 16-byte aligned");
+    const int64_t total = B * 3 * R * R / 4;
     const int64_t blocks = ceil_div(total, 256);
     MC_CHECK(blocks < (1ll << 31), "im2col: too large");
     if (image_is_u8)
