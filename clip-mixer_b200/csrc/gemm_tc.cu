@@ -392,41 +392,36 @@ constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C c
 template <int EPI>
 __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
                                                uint32_t taddr, uint32_t stage, float bias_m, bool row_ok, long long crow,
-                                               int m_base, int b, int n, int lane) {
+                                               int m_base, int b, int n, int lane, uint32_t zbar, uint32_t zphase,
+                                               int next_n) {
     uint32_t v[32];
-    const bool full = n + 32 <= g.N;
+    [[maybe_unused]] const bool full = n + 32 <= g.N;
     if constexpr (EPI == EPI_ACT_BWD) {
-        // saved pre-activation of this row (fp16): direct 256-bit loads, requested before the TMEM load is waited for
-        uint32_t z[2][8];
+        // The saved pre-activation chunk (fp16 [32 x 32], swizzle-64B) was requested by TMA one chunk ahead into
+        // the second half of the staging tile (see the epilogue loop); rows >= M / columns >= N arrive as zeros.
+        mbar_wait(zbar, zphase);
+        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+        uint32_t z[16];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) z[j][i] = 0u;
-        const __half* zp = g.zin + (long long)b * g.zin_bs + crow * g.ldzin + n;
-        if (row_ok) {
-            if (full && g.vec_ok) {
-                ldg256(zp, z[0]);
-                ldg256(zp + 16, z[1]);
-            } else {
-                const unsigned short* zs = reinterpret_cast<const unsigned short*>(zp);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t h = (n + i < g.N) ? (uint32_t)zs[i] : 0u;
-                    z[i >> 4][(i & 15) >> 1] |= h << ((i & 1) * 16);
-                }
-            }
+        for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(z[4 * j]), "=r"(z[4 * j + 1]), "=r"(z[4 * j + 2]), "=r"(z[4 * j + 3])
+                         : "r"(rowp + 2048 + ((j ^ sw) << 4)));
+        __syncwarp();
+        if (lane == 0 && next_n >= 0) {   // prefetch the next chunk's pre-activations
+            mbar_arrive_expect_tx(zbar, 2048);
+            tma_load_3d(stage + 2048, tmZ, zbar, next_n, m_base, b);
         }
         tmem_ld32(taddr, v);
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const float2 zz = unpack_h2(z[i >> 3][i & 7]);
+            const float2 zz = unpack_h2(z[i]);
             o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * gelu_grad_t(zz.x), __uint_as_float(v[2 * i + 1]) * gelu_grad_t(zz.y));
         }
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         fence_proxy_async_smem();
@@ -565,6 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t zin_bar[kEpiWarps];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
@@ -583,7 +579,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         if (g.tma_epi) {
             tma_prefetch_desc(&tmC);
-            if (g.zout != nullptr) tma_prefetch_desc(&tmZ);
+            if (g.zout != nullptr || g.zin != nullptr) tma_prefetch_desc(&tmZ);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -598,6 +594,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // pair mode: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
             mbar_init(smem_u32(&tempty_bar[s]), two ? 2 * kEpiWarps : kEpiWarps);
         }
+        for (int s = 0; s < kEpiWarps; ++s) mbar_init(smem_u32(&zin_bar[s]), 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -734,7 +731,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = warp - 4;
         const int q = e & 3;    // TMEM lane quarter == warp id % 4
         const int half = e >> 2;  // which 32-column chunks of every 64 this warp drains
-        uint32_t as = 0, aphase = 0;
+        uint32_t as = 0, aphase = 0, zphase = 0;
         for (int t = work0; t < g.num_tiles; t += work_stride) {
             const TileCoord tc = decode_tile(g, t, cta_rank);
             const int m = tc.tm * BM + q * 32 + lane;
@@ -743,17 +740,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long crow = g.row_remap > 0 ? (long long)m + m / g.row_remap + 1 : (long long)m;
             float bias_m = 0.f;
             if (g.bias_mode == MC_BIAS_M && row_ok) bias_m = g.bias[m];
+            const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
+            const uint32_t zbar = smem_u32(&zin_bar[e]);
+            if (EPI == EPI_ACT_BWD && g.tma_epi && lane == 0 && half * 32 < g.BN && n0 + half * 32 < g.N) {
+                // first pre-activation chunk of this tile: in flight while the tile's MMAs finish
+                mbar_arrive_expect_tx(zbar, 2048);
+                tma_load_3d(stage_buf + 2048, &tmZ, zbar, n0 + half * 32, tc.tm * BM + q * 32, tc.b);
+            }
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
-            const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
             for (int c = half * 32; c < g.BN; c += 64) {
                 const int nb = n0 + c;
                 if (nb >= g.N) break;  // warp-uniform
                 const int rem = g.N - nb;
                 if ((EPI == EPI_ACT_FWD || EPI == EPI_ACT_BWD || EPI == EPI_PLAIN) && g.tma_epi) {
+                    const int next_n = (c + 64 < g.BN && nb + 64 < g.N) ? nb + 64 : -1;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
-                                        nb, lane);
+                                        nb, lane, zbar, zphase, next_n);
+                    if (EPI == EPI_ACT_BWD) zphase ^= 1u;
                 } else if (EPI != EPI_GENERIC && rem >= 32) {
                     chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok);
                 } else {
@@ -1015,7 +1020,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 16 == 0) && (ld * esz) % 16 == 0 && (bs * esz) % 16 == 0);
     };
     g.tma_epi = allow_tma_epi && (epi == EPI_ACT_FWD || epi == EPI_ACT_BWD || epi == EPI_PLAIN) && p->row_remap == 0 &&
-                al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2);
+                al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2) &&
+                al16(p->zin, p->ldzin, p->zin_batch_stride, 2);
     const int epi_bytes = g.tma_epi ? kEpiWarps * (int)kEpiWarpBytes : 0;
     const int smem_budget = 225 * 1024 - epi_bytes;
     g.stages = smem_budget / g.stage_bytes;
@@ -1056,6 +1062,10 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         if (p->zout != nullptr) {
             rc = make_store_map(&tmZ, p->zout, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->N, p->M, g.out_batch, p->ldz,
                                 p->z_batch_stride, "Z");
+            if (rc != MC_OK) return rc;
+        } else if (epi == EPI_ACT_BWD) {   // the saved pre-activations are LOADED through the same box geometry
+            rc = make_store_map(&tmZ, const_cast<void*>(p->zin), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->N, p->M, g.out_batch,
+                                p->ldzin, p->zin_batch_stride, "Zin");
             if (rc != MC_OK) return rc;
         }
     }
