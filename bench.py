@@ -279,7 +279,13 @@ def main():
                                               f"torch fp32, {os.cpu_count()} threads), 3 timed iterations, {t * 1e3:.0f} ms each"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a captured CUDA graph can stall the interpreter's teardown:
+        # synchronise, meet at a barrier, flush, and leave without running destructors.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
