@@ -36,8 +36,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per k-block = 128 B = one swizzle row
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 12;                    // three per TMEM lane quarter
+constexpr int kThreads = 128 + kEpiWarps * 32;  // 512
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -76,11 +76,13 @@ struct TileCoord {
 
 // t indexes work items of a cluster; the CTA of rank r in the cluster takes m-tile tm_eff * cluster + r
 __device__ __forceinline__ TileCoord decode_tile(const GemmTcArgs& g, int t, int cta_rank) {
+    // n-tiles vary fastest: the CTAs working at any moment share a few A row-blocks and sweep the (small,
+    // L2-resident) B operand, so the big activation operand is streamed from DRAM once
     TileCoord c;
-    c.tm = (t % g.tiles_m_eff) * g.cluster + cta_rank;
-    t /= g.tiles_m_eff;
     c.tn = t % g.tiles_n;
     t /= g.tiles_n;
+    c.tm = (t % g.tiles_m_eff) * g.cluster + cta_rank;
+    t /= g.tiles_m_eff;
     c.b = t % g.out_batch;
     const int ks = t / g.out_batch;
     c.kb_begin = int((long long)ks * g.kb_total / g.split_k);
@@ -382,6 +384,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+constexpr int kChunkStride = 32 * (kEpiWarps / 4);   // columns between consecutive chunks of one epilogue warp
 constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C chunk (2 KB) + an fp16 Z chunk (2 KB)
 
 // One 32-column chunk leaving through shared memory and a TMA store: every lane owns one output row, writes it
@@ -471,6 +474,50 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             tma_store_3d(tmC, stage, n, m_base, b);
             if (g.zout != nullptr) tma_store_3d(tmZ, stage + 2048, n, m_base, b);
             bulk_commit();
+        }
+    } else if constexpr (EPI == EPI_RESID) {
+        // The fp32 residual chunk ([32 x 32], swizzle-128B) was requested by TMA one chunk ahead; the result
+        // leaves through direct 256-bit stores (write-only, nothing waits on them).
+        mbar_wait(zbar, zphase);
+        const uint32_t rowp = stage + lane * 128, sw = lane & 7;
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
+                         : "r"(rowp + ((j ^ sw) << 4)));
+        __syncwarp();
+        if (lane == 0 && next_n >= 0) {
+            mbar_arrive_expect_tx(zbar, 4096);
+            tma_load_3d(stage, tmZ, zbar, next_n, m_base, b);
+        }
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (!row_ok) return;
+        float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        if (full && g.vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o[8];
+                if (g.bias_mode == MC_BIAS_N) {
+                    float bv[8];
+                    ldg256f(g.bias + n + 8 * j, bv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]) + bv[i] + __uint_as_float(r[8 * j + i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]) + bias_m + __uint_as_float(r[8 * j + i]);
+                }
+                stg256f(cp + 8 * j, o);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (n + i < g.N) {
+                    const float bb = g.bias_mode == MC_BIAS_N ? g.bias[n + i] : bias_m;
+                    cp[i] = __uint_as_float(v[i]) + bb + __uint_as_float(r[i]);
+                }
+            }
         }
     } else {  // EPI_PLAIN: fp32 tile, plain store or reduce-add (accumulate / split-K)
         tmem_ld32(taddr, v);
@@ -578,8 +625,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (g.tma_epi) {
-            tma_prefetch_desc(&tmC);
-            if (g.zout != nullptr || g.zin != nullptr) tma_prefetch_desc(&tmZ);
+            if (EPI != EPI_RESID) tma_prefetch_desc(&tmC);
+            if (g.zout != nullptr || g.zin != nullptr || g.R != nullptr) tma_prefetch_desc(&tmZ);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -730,7 +777,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue =====================
         const int e = warp - 4;
         const int q = e & 3;    // TMEM lane quarter == warp id % 4
-        const int half = e >> 2;  // which 32-column chunks of every 64 this warp drains
+        const int half = e >> 2;  // which 32-column chunks of every kChunkStride this warp drains (0 .. kEpiWarps/4-1)
         uint32_t as = 0, aphase = 0, zphase = 0;
         for (int t = work0; t < g.num_tiles; t += work_stride) {
             const TileCoord tc = decode_tile(g, t, cta_rank);
@@ -742,23 +789,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (g.bias_mode == MC_BIAS_M && row_ok) bias_m = g.bias[m];
             const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
             const uint32_t zbar = smem_u32(&zin_bar[e]);
-            if (EPI == EPI_ACT_BWD && g.tma_epi && lane == 0 && half * 32 < g.BN && n0 + half * 32 < g.N) {
-                // first pre-activation chunk of this tile: in flight while the tile's MMAs finish
-                mbar_arrive_expect_tx(zbar, 2048);
-                tma_load_3d(stage_buf + 2048, &tmZ, zbar, n0 + half * 32, tc.tm * BM + q * 32, tc.b);
+            if ((EPI == EPI_ACT_BWD || EPI == EPI_RESID) && g.tma_epi && lane == 0 && half * 32 < g.BN &&
+                n0 + half * 32 < g.N) {
+                // first pre-activation / residual chunk of this tile: in flight while the tile's MMAs finish
+                const uint32_t bytes = EPI == EPI_RESID ? 4096u : 2048u;
+                mbar_arrive_expect_tx(zbar, bytes);
+                tma_load_3d(stage_buf + (EPI == EPI_RESID ? 0u : 2048u), &tmZ, zbar, n0 + half * 32, tc.tm * BM + q * 32, tc.b);
             }
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
-            for (int c = half * 32; c < g.BN; c += 64) {
+            for (int c = half * 32; c < g.BN; c += kChunkStride) {
                 const int nb = n0 + c;
                 if (nb >= g.N) break;  // warp-uniform
                 const int rem = g.N - nb;
-                if ((EPI == EPI_ACT_FWD || EPI == EPI_ACT_BWD || EPI == EPI_PLAIN) && g.tma_epi) {
-                    const int next_n = (c + 64 < g.BN && nb + 64 < g.N) ? nb + 64 : -1;
+                if (EPI != EPI_GENERIC && g.tma_epi) {
+                    const int next_n = (c + kChunkStride < g.BN && nb + kChunkStride < g.N) ? nb + kChunkStride : -1;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
                                         nb, lane, zbar, zphase, next_n);
-                    if (EPI == EPI_ACT_BWD) zphase ^= 1u;
+                    if (EPI == EPI_ACT_BWD || EPI == EPI_RESID) zphase ^= 1u;
                 } else if (EPI != EPI_GENERIC && rem >= 32) {
                     chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok);
                 } else {
@@ -788,7 +837,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             as ^= 1u;
             if (as == 0) aphase ^= 1u;
         }
-        if (g.tma_epi && lane == 0) bulk_wait_all();  // the staging tiles must outlive their TMA stores
+        if (g.tma_epi && EPI != EPI_RESID && lane == 0) bulk_wait_all();  // staging tiles must outlive their TMA stores
     }
 
     tc_fence_before();
@@ -1019,7 +1068,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     auto al16 = [](const void* q, long long ld, long long bs, int esz) {
         return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 16 == 0) && (ld * esz) % 16 == 0 && (bs * esz) % 16 == 0);
     };
-    g.tma_epi = allow_tma_epi && (epi == EPI_ACT_FWD || epi == EPI_ACT_BWD || epi == EPI_PLAIN) && p->row_remap == 0 &&
+    g.tma_epi = allow_tma_epi && epi != EPI_GENERIC && p->row_remap == 0 && al16(p->R, p->ldr, p->r_batch_stride, 4) &&
                 al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2) &&
                 al16(p->zin, p->ldzin, p->zin_batch_stride, 2);
     const int epi_bytes = g.tma_epi ? kEpiWarps * (int)kEpiWarpBytes : 0;
@@ -1054,7 +1103,11 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     CUtensorMap tmC, tmZ;
     memset(&tmC, 0, sizeof(tmC));
     memset(&tmZ, 0, sizeof(tmZ));
-    if (g.tma_epi) {
+    if (g.tma_epi && epi == EPI_RESID) {   // only the residual goes through TMA (loaded); C is stored directly
+        rc = make_store_map(&tmZ, const_cast<float*>(p->R), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->N, p->M, g.out_batch, p->ldr,
+                            p->r_batch_stride, "R");
+        if (rc != MC_OK) return rc;
+    } else if (g.tma_epi) {
         const int esz = c_bf16 ? 2 : 4;
         rc = make_store_map(&tmC, p->C, c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, esz, p->N,
                             p->M, g.out_batch, p->ldc, p->c_batch_stride, "C");
