@@ -38,7 +38,7 @@ TRAIN_GFLOP_PER_SAMPLE = 32.166          # GEMM FLOPs of one trainin
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--per-gpu-batch", type=int, default=PER_GPU_BATCH)
@@ -128,7 +128,7 @@ def workload_config(args, world):
                         f"loss + backward + clip_grad_norm + AdamW, {args.per_gpu_batch} samples per GPU",
             "global_batch": args.per_gpu_batch * world, "image": "224x224 uint8", "text_tokens": 77,
             "parallelism": f"dp{world}", "l2_hygiene": "per-step working set (~10 GB of activations) >> 126 MB L2",
-            "cuda_graph": not args.no_graph}
+            "cuda_graph": not args.no_graph, "streams": "image and text towers on two streams"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -177,7 +177,8 @@ def main():
     for _ in range(args.warmup):
         stepper.step(images, texts)
     barrier()
-    eager = FusedTrainStep(model, opt, dp, total_steps=10 ** 6, use_cuda_graph=False)
+    # single-stream, eager twin of the step: counts launches and carries the per-kernel CUDA-event timing
+    eager = FusedTrainStep(model, opt, dp, total_steps=10 ** 6, use_cuda_graph=False, overlap_towers=False)
     ops.reset_launch_count()
     eager.step(images, texts)
     launches_per_step = ops.launch_count()

@@ -31,7 +31,8 @@ class FusedTrainStep:
     this rank; nothing is read back to the host."""
 
     def __init__(self, model, optimizer: Optional[FusedAdamW] = None, dp: Optional[DataParallel] = None,
-                 total_steps: int = 10 ** 9, max_lr: float = 5e-4, warmup_steps: int = 2, use_cuda_graph: bool = False):
+                 total_steps: int = 10 ** 9, max_lr: float = 5e-4, warmup_steps: int = 2, use_cuda_graph: bool = False,
+                 overlap_towers: bool = True, micro_batch: Optional[int] = None):
         self.model = model
         self.dp = dp
         self.world = dp.world if dp is not None else 1
@@ -50,6 +51,16 @@ class FusedTrainStep:
         self.static_images = self.static_texts = None
         self._bufs = {}
         self.clamp_ddp_branch = self.world > 1     # training.py:174-178 has two different clamps
+        self._side = None
+        self.overlap_towers = overlap_towers
+        self.micro_batch = micro_batch
+
+    def _side_stream(self):
+        if not self.overlap_towers:
+            return torch.cuda.current_stream()      # single-stream schedule (per-kernel timing passes)
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     # ---- schedule -----------------------------------------------------------------------------------
     def current_lr(self):
@@ -64,8 +75,21 @@ class FusedTrainStep:
         E = model._cfg["embed_dim"]
         store.flat_g.zero_()                                                        # optimizer.zero_grad()  :144
         model._prepare_weights()
-        ws_i = img_t.forward(images, prec, True)                                    # model(images, texts)   :156
-        ws_t = txt_t.forward(texts, prec, True)
+        if self.micro_batch is not None and n > self.micro_batch:
+            self._micro_batched_backward(images, texts)
+            self._finish_step()
+            return
+        # The two towers are independent until the loss: they run on two streams so that one tower's kernels fill
+        # the SMs the other leaves idle (partial last waves of the persistent GEMMs, HBM-bound row kernels).
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            ws_t = txt_t.forward(texts, prec, True)                                 # model(images, texts)   :156
+        ws_i = img_t.forward(images, prec, True)
+        main.wait_stream(side)
         if self.dp is not None and self.world > 1:
             ui_all, ut_all = self.dp.gather(ws_i.u_feat, ws_t.u_feat)               # accelerator.gather     :158-159
         else:
@@ -82,8 +106,17 @@ class FusedTrainStep:
                          self.loss, b["dui"], b["dut"], store.grad_view("logit_scale"), b["ws"])   # :162-170
         hook_t = self.dp.after_block_hook("text") if self.dp is not None else None
         hook_i = self.dp.after_block_hook("image") if self.dp is not None else None
-        txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)                    # accelerator.backward   :170
+        fork2 = torch.cuda.Event()
+        fork2.record(main)
+        side.wait_event(fork2)
+        with torch.cuda.stream(side):
+            txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)                # accelerator.backward   :170
         img_t.backward(ws_i, b["dui"], prec, after_block=hook_i)
+        main.wait_stream(side)
+        self._finish_step()
+
+    def _finish_step(self):
+        model = self.model
         if self.dp is not None:
             self.dp.finish()
         with torch.no_grad():                                                       # clamp                  :173-178
@@ -92,6 +125,52 @@ class FusedTrainStep:
             else:
                 model.logit_scale.data.clamp_(max=100)
         self.opt.launch(grad_mul=1.0)                                               # clip + step            :181,185
+
+    def _micro_batched_backward(self, images, texts):
+        """Global-batch contrastive step when n samples do not fit at once (config 3: 32768 over 2-4 GPUs,
+        SURVEY 7.3-7).  Because the gathered features are detached (training.py:158-159) this is EXACT, not an
+        approximation: pass 1 computes every local feature without saving activations, the features are gathered,
+        pass 2 re-runs each micro-batch with activations and back-propagates its rows against the cached global
+        features (labels offset by rank*n + k*m)."""
+        model, store = self.model, self.store
+        prec = model._precision
+        img_t, txt_t = model._towers["image"], model._towers["text"]
+        n, m = images.shape[0], self.micro_batch
+        if n % m:
+            raise MixerClipError(f"per-rank batch {n} must be a multiple of micro_batch {m}")
+        K, E, dev = n // m, model._cfg["embed_dim"], store.device
+        key = ("mb", n, m)
+        if key not in self._bufs:
+            self._bufs[key] = dict(ui=torch.empty(n, E, device=dev), ut=torch.empty(n, E, device=dev),
+                                   dui=torch.empty(m, E, device=dev), dut=torch.empty(m, E, device=dev),
+                                   loss=torch.zeros(1, device=dev))
+        b = self._bufs[key]
+        for k in range(K):                                                          # pass 1: features only
+            sl = slice(k * m, (k + 1) * m)
+            b["ui"][sl].copy_(img_t.forward(images[sl], prec, False).u_feat)
+            b["ut"][sl].copy_(txt_t.forward(texts[sl], prec, False).u_feat)
+        if self.dp is not None and self.world > 1:
+            ui_all, ut_all = self.dp.gather(b["ui"], b["ut"])
+        else:
+            ui_all, ut_all = b["ui"], b["ut"]
+        N = ui_all.shape[0]
+        if "ws" not in b or b["ws_key"] != (m, N):
+            b["ws"] = torch.empty(ops.head_workspace_bytes(m, N, E) // 4, device=dev)
+            b["ws_key"] = (m, N)
+        self.loss.zero_()
+        for k in range(K):                                                          # pass 2: activations + backward
+            sl = slice(k * m, (k + 1) * m)
+            last = k == K - 1
+            ws_i = img_t.forward(images[sl], prec, True)
+            ws_t = txt_t.forward(texts[sl], prec, True)
+            b["loss"].zero_()
+            ops.head_fwd_bwd(ws_i.u_feat, ws_t.u_feat, ui_all, ut_all, model.logit_scale, m, N, E, self.rank * K + k,
+                             m / n, b["loss"], b["dui"], b["dut"], store.grad_view("logit_scale"), b["ws"])
+            self.loss.add_(b["loss"], alpha=m / n)
+            hook_t = self.dp.after_block_hook("text") if (self.dp is not None and last) else None
+            hook_i = self.dp.after_block_hook("image") if (self.dp is not None and last) else None
+            txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)
+            img_t.backward(ws_i, b["dui"], prec, after_block=hook_i)
 
     def step(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
         if not (images.is_cuda and texts.is_cuda):

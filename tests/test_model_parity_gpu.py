@@ -203,3 +203,46 @@ def test_b32_full_size_vs_oracle(precision):
     assert sum(p.numel() for p in model.parameters()) == 111_060_389          # README.md:19 / SURVEY 0.2
     out = reference_style_step(model, image.to(DEV), text.to(DEV))
     check(out, truth, TOL[precision], f"B32/{precision}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_b16_token_mixing_heavy_shape_vs_oracle(precision):
+    """BASELINE.json configs[3] architecture (patch 16 -> 197 image tokens, token-mix 197 -> 788 -> 197), 2+2 layers,
+    batch 4, against the fp64 oracle."""
+    from oracle import mixer_clip_oracle as O
+    cfg = dict(O.CONFIGS["B16"])
+    cfg["vision_layers"] = cfg["transformer_layers"] = 2
+    sd = O.seeded_state_dict(cfg, seed=2)
+    image, text = O.synthetic_batch(cfg, 4, seed=3)
+    torch.set_num_threads(os.cpu_count())
+    truth = O.loss_and_grads({k: v.double() for k, v in sd.items()}, image.double(), text)
+    model = _build(cfg, sd, precision)
+    out = reference_style_step(model, image.to(DEV), text.to(DEV))
+    check(out, truth, TOL[precision], f"B16x2/{precision}")
+
+
+def test_zero_shot_scoring_matches_oracle():
+    """validation.py:119-139 shape: class prompts -> classifier, images -> 100 * f @ W -> top-k."""
+    from clip_mixer_b200.zeroshot import accuracy, zeroshot_classifier, zeroshot_logits
+    from oracle import mixer_clip_oracle as O
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    model = _build(cfg, sd, "fp32").eval()
+    classes, templates = 7, 5
+    prompts = [O.synthetic_batch(cfg, templates, seed=100 + c)[1] for c in range(classes)]
+    images, _ = O.synthetic_batch(cfg, 9, seed=50)
+    W = zeroshot_classifier(model, [p.to(DEV) for p in prompts])
+    logits = zeroshot_logits(model, images.to(DEV), W)
+    cols = []
+    for p in prompts:
+        e = O.encode_text(sd, p)
+        e = e / e.norm(dim=-1, keepdim=True)
+        e = e.mean(0)
+        cols.append(e / e.norm())
+    Wref = torch.stack(cols, 1)
+    f = O.encode_image(sd, images)
+    ref = 100.0 * (f / f.norm(dim=-1, keepdim=True)) @ Wref
+    assert O.l2_rel(W, Wref) <= 1e-5 and O.l2_rel(logits, ref) <= 1e-5
+    target = ref.argmax(1).to(DEV)
+    top1, top5 = accuracy(logits, target)
+    assert top1 == 9.0 and top5 == 9.0

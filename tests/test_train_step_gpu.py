@@ -97,3 +97,26 @@ def test_cuda_graph_replay_equals_eager():
     for k in p0:
         d = float((p0[k] - p1[k]).double().norm() / p0[k].double().norm().clamp_min(1e-30))
         assert d <= 1e-3, (k, d)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_micro_batched_step_is_exact(precision, tol):
+    """The detached gather makes micro-batching exact: gradients of a step on 8 samples in micro
+    batches of 2 equal those of the one-shot step (and the oracle's)."""
+    from clip_mixer_b200.training import FusedTrainStep
+    from oracle import mixer_clip_oracle as O
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    image, text = O.synthetic_batch(cfg, 8, seed=1)
+    truth = O.loss_and_grads({k: v.double() for k, v in sd.items()}, image.double(), text)
+    model = _model(cfg, sd, precision)
+    stepper = FusedTrainStep(model, total_steps=100, micro_batch=2)
+    loss = float(stepper.step(image.to(DEV), text.to(DEV)))
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    assert abs(loss - float(truth["loss"])) <= tol * abs(float(truth["loss"]))
+    worst, fails = O.compare_grads(grads, truth["grads"], tol)
+    cond = float(truth["logits_per_image"].diag().abs().mean())
+    fails = [f for f in fails if not (f[0] == "logit_scale" and
+                                      abs(float(grads["logit_scale"]) - float(truth["grads"]["logit_scale"])) <= tol * cond)]
+    print(f"[micro-batch/{precision}] worst grad err {worst:.2e}")
+    assert not fails, fails[:5]

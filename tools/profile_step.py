@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     model = CLIP(**_MODELS[args.model], useTransformer=False).to(dev).train()
-    stepper = FusedTrainStep(model, use_cuda_graph=False)
+    stepper = FusedTrainStep(model, use_cuda_graph=False, overlap_towers=False)
     images, texts = synthetic_batch(model._cfg, args.batch, 1000, dev)
     for _ in range(args.warmup):
         stepper.step(images, texts)
