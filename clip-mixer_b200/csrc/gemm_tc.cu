@@ -250,6 +250,29 @@ __device__ __forceinline__ float gelu_grad_t(float z) {
     return fmaf(fmaf(-w, s, w), s, s);  // s + w*s*(1-s)
 }
 
+// Packed (2 x fp32 per instruction, FFMA2 / FMUL2 / FADD2) versions for the staged epilogues, which are
+// instruction-issue bound on the token-mixing shapes (profiles/r1d): QuickGELU = hx + hx*tanh(0.851x).
+__device__ __forceinline__ float2 gelu2(float2 x) {
+    const float2 a = __fmul2_rn(x, make_float2(0.851f, 0.851f));
+    const float2 t = make_float2(tanh_approx(a.x), tanh_approx(a.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, t, hx);
+}
+__device__ __forceinline__ float2 gelu_grad2(float2 z) {
+    const float2 a = __fmul2_rn(z, make_float2(-2.4554669595930157f, -2.4554669595930157f));   // -1.702*log2(e)*z
+    float ex, ey, sx, sy;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(a.y));
+    const float2 den = __fadd2_rn(make_float2(ex, ey), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sx) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sy) : "f"(den.y));
+    const float2 s = make_float2(sx, sy);
+    const float2 w = __fmul2_rn(z, make_float2(kGeluA, kGeluA));
+    const float2 nw = __fmul2_rn(z, make_float2(-kGeluA, -kGeluA));
+    const float2 t1 = __ffma2_rn(nw, s, w);      // w (1 - s)
+    return __ffma2_rn(t1, s, s);                 // s + w s (1 - s)
+}
+
 // One full 32-column chunk (all columns valid, 32-byte aligned rows), specialised per epilogue kind.
 // Global operands of the chunk (residual / saved pre-activation) are requested BEFORE the TMEM load is
 // waited for, so their latency overlaps it.
@@ -420,8 +443,9 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
         uint32_t o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const float2 zz = unpack_h2(z[i]);
-            o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * gelu_grad_t(zz.x), __uint_as_float(v[2 * i + 1]) * gelu_grad_t(zz.y));
+            const float2 gp = gelu_grad2(unpack_h2(z[i]));
+            const float2 r = __fmul2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), gp);
+            o[i] = pack_bf16x2(r.x, r.y);
         }
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
@@ -436,7 +460,7 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
     } else if constexpr (EPI == EPI_ACT_FWD) {
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        float x[32];
+        float2 x[16];
         if (g.bias_mode == MC_BIAS_N) {
             if (full && g.vec_ok) {
 #pragma unroll
@@ -444,15 +468,20 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
                     float bv[8];
                     ldg256f(g.bias + n + 8 * j, bv);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) x[8 * j + i] = __uint_as_float(v[8 * j + i]) + bv[i];
+                    for (int i = 0; i < 4; ++i)
+                        x[4 * j + i] = __fadd2_rn(make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1])),
+                                                  make_float2(bv[2 * i], bv[2 * i + 1]));
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + (n + i < g.N ? g.bias[n + i] : 0.f);
+                for (int i = 0; i < 16; ++i)
+                    x[i] = make_float2(__uint_as_float(v[2 * i]) + (n + 2 * i < g.N ? g.bias[n + 2 * i] : 0.f),
+                                       __uint_as_float(v[2 * i + 1]) + (n + 2 * i + 1 < g.N ? g.bias[n + 2 * i + 1] : 0.f));
             }
         } else {
+            const float2 bm = make_float2(bias_m, bias_m);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + bias_m;
+            for (int i = 0; i < 16; ++i) x[i] = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bm);
         }
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
@@ -460,14 +489,17 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
         if (g.zout != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                sts128(rowp + 2048 + ((j ^ sw) << 4), pack_h2_sat(x[8 * j], x[8 * j + 1]), pack_h2_sat(x[8 * j + 2], x[8 * j + 3]),
-                       pack_h2_sat(x[8 * j + 4], x[8 * j + 5]), pack_h2_sat(x[8 * j + 6], x[8 * j + 7]));
+                sts128(rowp + 2048 + ((j ^ sw) << 4), pack_h2_sat(x[4 * j].x, x[4 * j].y), pack_h2_sat(x[4 * j + 1].x, x[4 * j + 1].y),
+                       pack_h2_sat(x[4 * j + 2].x, x[4 * j + 2].y), pack_h2_sat(x[4 * j + 3].x, x[4 * j + 3].y));
+        }
+        uint32_t h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 y = gelu2(x[i]);
+            h[i] = pack_bf16x2(y.x, y.y);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            sts128(rowp + ((j ^ sw) << 4), pack_bf16x2(gelu_t(x[8 * j]), gelu_t(x[8 * j + 1])),
-                   pack_bf16x2(gelu_t(x[8 * j + 2]), gelu_t(x[8 * j + 3])), pack_bf16x2(gelu_t(x[8 * j + 4]), gelu_t(x[8 * j + 5])),
-                   pack_bf16x2(gelu_t(x[8 * j + 6]), gelu_t(x[8 * j + 7])));
+        for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
