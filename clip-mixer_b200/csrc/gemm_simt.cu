@@ -22,6 +22,7 @@ struct SimtArgs {
     const float* zin; long long ldzin, zin_bs;
     int act;
     const float* R; long long ldr, r_bs;
+    float* rowsum_out;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
         const int m = m0 + ty * 4 + i;
         if (m >= g.M) continue;
         const long long crow = g.row_remap > 0 ? (long long)m + m / g.row_remap + 1 : (long long)m;
+        float rsum = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
@@ -90,7 +92,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
             if (g.R) x += g.R[(long long)ob * g.r_bs + crow * g.ldr + n];
             float* cp = g.C + (long long)ob * g.c_bs + crow * g.ldc + n;
             *cp = g.accumulate ? *cp + x : x;
+            rsum += x;
         }
+        if (g.rowsum_out != nullptr) atomicAdd(g.rowsum_out + m, rsum);
     }
 }
 
@@ -122,6 +126,7 @@ extern "C" int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream_) {
     g.zout = reinterpret_cast<float*>(p->zout); g.ldz = p->ldz; g.z_bs = p->z_batch_stride;
     g.zin = reinterpret_cast<const float*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
+    g.rowsum_out = p->rowsum_out;
     const long long tiles = ceil_div(p->M, TM) * ceil_div(p->N, TN);
     MC_CHECK(tiles < (1ll << 31) && g.out_batch < 65536, "simt gemm: grid too large");
     dim3 grid((unsigned)tiles, (unsigned)g.out_batch, 1);

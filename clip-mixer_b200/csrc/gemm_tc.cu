@@ -68,6 +68,7 @@ struct GemmTcArgs {
     int act;
     const float* R;
     long long ldr, r_bs;
+    float* rowsum_out;   // optional: rowsum_out[m] += sum over (batch, n) of the stored value
 };
 
 struct TileCoord {
@@ -100,7 +101,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(
 
 // ---- epilogue on 8 consecutive columns held in registers ----------------------------------------
 __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], float bias_m, long long crow, int b,
-                                          int n, int ncols, bool vec) {
+                                          int n, int ncols, bool vec, float& rsum) {
     // bias
     if (g.bias_mode == MC_BIAS_N) {
         if (vec) {
@@ -163,6 +164,11 @@ __device__ __forceinline__ void epilogue8(const GemmTcArgs& g, float (&x)[8], fl
             for (int j = 0; j < 8; ++j)
                 if (j < ncols) x[j] += rp[j];
         }
+    }
+    if (g.rowsum_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < ncols) rsum += x[j];
     }
     // store
     if (g.c_bf16) {
@@ -278,7 +284,7 @@ __device__ __forceinline__ float2 gelu_grad2(float2 z) {
 // waited for, so their latency overlaps it.
 template <int EPI>
 __device__ __forceinline__ void chunk32(const GemmTcArgs& g, uint32_t taddr, float bias_m, long long crow, int b, int n,
-                                        bool ok) {
+                                        bool ok, float& rsum) {
     // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane executes it; only the global accesses are
     // predicated on the row being inside M.
     uint32_t v[32];
@@ -326,6 +332,7 @@ __device__ __forceinline__ void chunk32(const GemmTcArgs& g, uint32_t taddr, flo
                 const float2 zz = unpack_h2(z[j][i]);
                 const float a = __uint_as_float(v[16 * j + 2 * i]) * gelu_grad_t(zz.x);
                 const float c = __uint_as_float(v[16 * j + 2 * i + 1]) * gelu_grad_t(zz.y);
+                rsum += a + c;
                 o[i] = pack_bf16x2(a, c);
             }
             stg256(cp + 16 * j, o);
@@ -419,7 +426,7 @@ template <int EPI>
 __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
                                                uint32_t taddr, uint32_t stage, float bias_m, bool row_ok, long long crow,
                                                int m_base, int b, int n, int lane, uint32_t zbar, uint32_t zphase,
-                                               int next_n) {
+                                               int next_n, float& rsum) {
     uint32_t v[32];
     [[maybe_unused]] const bool full = n + 32 <= g.N;
     if constexpr (EPI == EPI_ACT_BWD) {
@@ -446,6 +453,8 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             const float2 gp = gelu_grad2(unpack_h2(z[i]));
             const float2 r = __fmul2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), gp);
             o[i] = pack_bf16x2(r.x, r.y);
+            if (full) rsum += r.x + r.y;                     // columns >= N hold garbage accumulators
+            else rsum += (n + 2 * i < g.N ? r.x : 0.f) + (n + 2 * i + 1 < g.N ? r.y : 0.f);
         }
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
@@ -811,6 +820,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = e & 3;    // TMEM lane quarter == warp id % 4
         const int half = e >> 2;  // which 32-column chunks of every kChunkStride this warp drains (0 .. kEpiWarps/4-1)
         uint32_t as = 0, aphase = 0, zphase = 0;
+        float rs_acc[2] = {0.f, 0.f};   // fused row sums, one slot per m-tile this CTA can meet (tiles_m_eff <= 2)
+        int rs_row[2] = {-1, -1};
         for (int t = work0; t < g.num_tiles; t += work_stride) {
             const TileCoord tc = decode_tile(g, t, cta_rank);
             const int m = tc.tm * BM + q * 32 + lane;
@@ -831,6 +842,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
+            float rsum = 0.f;
             for (int c = half * 32; c < g.BN; c += kChunkStride) {
                 const int nb = n0 + c;
                 if (nb >= g.N) break;  // warp-uniform
@@ -838,10 +850,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (EPI != EPI_GENERIC && g.tma_epi) {
                     const int next_n = (c + kChunkStride < g.BN && nb + kChunkStride < g.N) ? nb + kChunkStride : -1;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
-                                        nb, lane, zbar, zphase, next_n);
+                                        nb, lane, zbar, zphase, next_n, rsum);
                     if (EPI == EPI_ACT_BWD || EPI == EPI_RESID) zphase ^= 1u;
                 } else if (EPI != EPI_GENERIC && rem >= 32) {
-                    chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok);
+                    chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok, rsum);
                 } else {
                     uint32_t v[32];
                     tmem_ld32(t_row + c, v);
@@ -854,10 +866,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 float x[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j8 * 8 + j]);
-                                epilogue8(g, x, bias_m, crow, tc.b, nb + j8 * 8, ncols, g.vec_ok && ncols >= 8);
+                                epilogue8(g, x, bias_m, crow, tc.b, nb + j8 * 8, ncols, g.vec_ok && ncols >= 8, rsum);
                             }
                         }
                     }
+                }
+            }
+            if (g.rowsum_out != nullptr && row_ok) {
+                if (g.tiles_m_eff <= 2) {
+                    const int slot = (tc.tm / g.cluster) & 1;
+                    rs_acc[slot] += rsum;
+                    rs_row[slot] = m;
+                } else {
+                    atomicAdd(g.rowsum_out + m, rsum);
                 }
             }
             tc_fence_before();
@@ -868,6 +889,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             as ^= 1u;
             if (as == 0) aphase ^= 1u;
+        }
+        if (g.rowsum_out != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (rs_row[k] >= 0) atomicAdd(g.rowsum_out + rs_row[k], rs_acc[k]);
         }
         if (g.tma_epi && EPI != EPI_RESID && lane == 0) bulk_wait_all();  // staging tiles must outlive their TMA stores
     }
@@ -1118,6 +1144,10 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.zout = reinterpret_cast<__half*>(p->zout); g.ldz = p->ldz; g.z_bs = p->z_batch_stride;
     g.zin = reinterpret_cast<const __half*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
+    g.rowsum_out = p->rowsum_out;
+    MC_CHECK(p->rowsum_out == nullptr || epi == EPI_ACT_BWD || epi == EPI_GENERIC,
+             "gemm: rowsum_out is supported with the GELU-backward and generic epilogues only");
+    MC_CHECK(p->rowsum_out == nullptr || (p->row_remap == 0 && !g.k_spans_batch), "gemm: rowsum_out with row_remap / k_spans_batch");
     // vector (8-column) epilogue accesses need every touched row start to be 32-byte aligned
     auto al = [](const void* q, long long ld, long long bs, int esz) {
         return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 32 == 0) && (ld * esz) % 32 == 0 && (bs * esz) % 32 == 0);

@@ -180,11 +180,9 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm backward, dense case (the 48 block-level calls of a step), split in two HBM-bound kernels:
-//   rows: dx = dres + LNbwd(dy)  (+ act copy, + row sums) - no cross-row accumulators, so few registers and
-//         full occupancy;
-//   cols: dgamma, dbeta, column sums of dx - threads own columns, loop over rows (operands just written by
-//         the row kernel are mostly L2-resident).
+// LayerNorm backward, dense case (the 48 block-level calls of a step): dx = dres + LNbwd(dy) (+ act copy, + row
+// sums) with the column accumulators (dgamma, dbeta, column sums of dx) kept in shared memory, so the operands
+// are read from HBM exactly once and the register footprint stays that of a plain row kernel.
 // The fused kernel above keeps serving the gather / class-token variants (3 calls per step).
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
@@ -192,96 +190,88 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                    float* __restrict__ dx, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
-                   long long rowsum_period, long long rows, int D) {
-    const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float mu = mean[row], rs = rstd[row];
-    const float* xr = x + row * (long long)D;
-    const float* dyr = dy + row * (long long)D;
-    float4 xh[VPL], d[VPL];
-    float s1 = 0.f, s2 = 0.f;
+                   long long rowsum_period, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ colsum_out, long long rows, int D) {
+    // Persistent over rows.  The column accumulators (dgamma, dbeta, column sums of dx) live in shared memory,
+    // one private copy per warp (lane-owned columns: conflict-free read-modify-write), so the kernel keeps the
+    // register footprint of a plain row kernel (full occupancy) and the operands are read from HBM exactly once.
+    extern __shared__ float acc_sm[];                       // [warp][3][VPL*128]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W = VPL * 128;
+    float* my = acc_sm + (size_t)warp * 3 * W;
+    const bool want_cs = colsum_out != nullptr;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const int c = (i * 32 + lane) * 4;
-        if (c < D) {
-            const float4 xv = ld4(xr + c), g = ld4(dyr + c), gm = ld4(gamma + c);
-            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-            d[i] = make_float4(g.x * gm.x, g.y * gm.y, g.z * gm.z, g.w * gm.w);
-            s1 += d[i].x + d[i].y + d[i].z + d[i].w;
-            s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
-        } else {
-            xh[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        st4(my + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(my + W + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(my + 2 * W + c, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     const float invD = 1.0f / D;
-    const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
-    float rsum = 0.f;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + warp; row < rows;
+         row += (long long)gridDim.x * kWarpsPerBlock) {
+        const float mu = mean[row], rs = rstd[row];
+        const float* xr = x + row * (long long)D;
+        const float* dyr = dy + row * (long long)D;
+        float4 xh[VPL], d[VPL];
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < D) {
-            float4 o;
-            o.x = rs * (d[i].x - c1 - xh[i].x * c2);
-            o.y = rs * (d[i].y - c1 - xh[i].y * c2);
-            o.z = rs * (d[i].z - c1 - xh[i].z * c2);
-            o.w = rs * (d[i].w - c1 - xh[i].w * c2);
-            if (dres != nullptr) {
-                const float4 r = ld4(dres + row * (long long)D + c);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
-            st4(dx + row * (long long)D + c, o);
-            if (dx_act != nullptr) st_act4(dx_act, act_dtype, row * (long long)D + c, o);
-            rsum += o.x + o.y + o.z + o.w;
-        }
-    }
-    if (rowsum_out != nullptr) {
-        rsum = warp_sum(rsum);
-        if (lane == 0) atomicAdd(rowsum_out + row % rowsum_period, rsum);
-    }
-}
-
-// block: 64 column groups (float4) x 4 row lanes; grid (ceil(D/256), row chunks)
-__global__ void __launch_bounds__(256)
-ln_bwd_cols_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, const float* __restrict__ dx, float* __restrict__ dgamma,
-                   float* __restrict__ dbeta, float* __restrict__ colsum_out, long long rows, int D,
-                   long long rows_per_block) {
-    __shared__ float4 red[3][4][64];
-    const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
-    const int c = (blockIdx.x * 64 + cg) * 4;
-    const long long r0 = (long long)blockIdx.y * rows_per_block;
-    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
-    if (c < D) {
-#pragma unroll 4
-        for (long long r = r0 + rl; r < r1; r += 4) {
-            const float4 g = ld4(dy + r * D + c), xv = ld4(x + r * D + c);
-            const float mu = mean[r], rs = rstd[r];
-            ag.x += g.x * (xv.x - mu) * rs; ag.y += g.y * (xv.y - mu) * rs;
-            ag.z += g.z * (xv.z - mu) * rs; ag.w += g.w * (xv.w - mu) * rs;
-            ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
-            if (colsum_out != nullptr) {
-                const float4 o = ld4(dx + r * D + c);
-                ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                const float4 xv = ld4(xr + c), g = ld4(dyr + c), gm = ld4(gamma + c);
+                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                float4 a = ld4(my + c), bsum = ld4(my + W + c);
+                a.x += g.x * xh[i].x; a.y += g.y * xh[i].y; a.z += g.z * xh[i].z; a.w += g.w * xh[i].w;
+                bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+                st4(my + c, a);
+                st4(my + W + c, bsum);
+                d[i] = make_float4(g.x * gm.x, g.y * gm.y, g.z * gm.z, g.w * gm.w);
+                s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+                s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
+            } else {
+                xh[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
+        float rsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float4 o;
+                o.x = rs * (d[i].x - c1 - xh[i].x * c2);
+                o.y = rs * (d[i].y - c1 - xh[i].y * c2);
+                o.z = rs * (d[i].z - c1 - xh[i].z * c2);
+                o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+                if (dres != nullptr) {
+                    const float4 r = ld4(dres + row * (long long)D + c);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                st4(dx + row * (long long)D + c, o);
+                if (dx_act != nullptr) st_act4(dx_act, act_dtype, row * (long long)D + c, o);
+                if (want_cs) {
+                    float4 cs = ld4(my + 2 * W + c);
+                    cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                    st4(my + 2 * W + c, cs);
+                }
+                rsum += o.x + o.y + o.z + o.w;
+            }
+        }
+        if (rowsum_out != nullptr) {
+            rsum = warp_sum(rsum);
+            if (lane == 0) atomicAdd(rowsum_out + row % rowsum_period, rsum);
+        }
     }
-    red[0][rl][cg] = ag; red[1][rl][cg] = ab; red[2][rl][cg] = ac;
     __syncthreads();
-    if (rl == 0 && c < D) {
+    for (int idx = threadIdx.x; idx < 3 * D; idx += blockDim.x) {
+        const int which = idx / D, c = idx - which * D;
+        float* out = which == 0 ? dgamma : which == 1 ? dbeta : colsum_out;
+        if (out == nullptr) continue;
+        float sum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            float* out = w == 0 ? dgamma : w == 1 ? dbeta : colsum_out;
-            if (out == nullptr) continue;
-            float4 a = red[w][0][cg];
-#pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                const float4 b = red[w][k][cg];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            atomicAdd(reinterpret_cast<float4*>(out + c), a);
-        }
+        for (int w = 0; w < kWarpsPerBlock; ++w) sum += acc_sm[(size_t)w * 3 * W + which * W + c];
+        atomicAdd(out + c, sum);
     }
 }
 
@@ -622,17 +612,23 @@ extern "C" int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, 
     const bool dense = row_index == nullptr && cls == nullptr && dcls == nullptr && dx != nullptr && x_row_stride == D &&
                        dx_row_stride == D && D % 4 == 0 && aligned16(dgamma) && aligned16(dbeta) && aligned16(colsum_out);
     if (dense) {
-        const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
-        MC_DISPATCH_VPL(vpl, (ln_bwd_rows_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-                                 dy, x, mean, rstd, gamma, dres, dx, dx_act, act_dtype, rowsum_out, rowsum_period, rows, (int)D)));
-        MC_CUDA(cudaGetLastError());
-        const int64_t col_blocks = ceil_div(D, 256);
-        int64_t row_blocks = ceil_div((int64_t)sm_count() * 3, col_blocks);
-        if (row_blocks > ceil_div(rows, 16)) row_blocks = ceil_div(rows, 16);
-        if (row_blocks < 1) row_blocks = 1;
-        const int64_t rpb = ceil_div(ceil_div(rows, row_blocks), 4) * 4;
-        dim3 g2((unsigned)col_blocks, (unsigned)ceil_div(rows, rpb));
-        ln_bwd_cols_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, dx, dgamma, dbeta, colsum_out, rows, (int)D, rpb);
+        const size_t smem = (size_t)kWarpsPerBlock * 3 * vpl * 128 * sizeof(float);   // <= 96 KB (VPL 8)
+        int per_sm = (int)((200 * 1024) / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int64_t blocks = ceil_div(rows, kWarpsPerBlock);
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        if (blocks > cap) blocks = cap;
+        MC_DISPATCH_VPL(vpl, {
+            static bool attr_set = false;
+            if (!attr_set) {
+                MC_CUDA(cudaFuncSetAttribute(ln_bwd_rows_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr_set = true;
+            }
+            ln_bwd_rows_kernel<VPL><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+                dy, x, mean, rstd, gamma, dres, dx, dx_act, act_dtype, rowsum_out, rowsum_period, dgamma, dbeta, colsum_out,
+                rows, (int)D);
+        });
         MC_CUDA(cudaGetLastError());
         return MC_OK;
     }

@@ -283,14 +283,14 @@ class TowerRT:
         # ---- token mix:  Y = X + W2 g(W1 U + b1) + b2   (per sample, U = LN1(X)) ----
         w2, ld2 = self.wop(pre + "token_mix_seq.lin2.weight", prec)                   # [P, 4P]
         ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
-                 act=ACT_GELU_BWD, zin=z1, ldzin=D, zin_bs=4 * P * D)                  # dZ1 = (W2^T dY) * g'(Z1)
+                 act=ACT_GELU_BWD, zin=z1, ldzin=D, zin_bs=4 * P * D,
+                 rowsum_out=G(pre + "token_mix_seq.lin1.bias"))                        # dZ1 = (W2^T dY) * g'(Z1); db1 fused
         g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
         ops.gemm(eng, P, 4 * P, D, B, dcur_a, MAJOR_K, D, P * D, h1, MAJOR_K, D, 4 * P * D, g2, ldg2, 0,
                  k_spans_batch=True, accumulate=True, split_k=0)                       # dW2 += sum_b dY H1^T
         g1, ldg1 = st.grad2d(pre + "token_mix_seq.lin1.weight")
         ops.gemm(eng, 4 * P, P, D, B, dz1, MAJOR_K, D, 4 * P * D, u, MAJOR_K, D, P * D, g1, ldg1, 0,
                  k_spans_batch=True, accumulate=True, split_k=0)                       # dW1 += sum_b dZ1 U^T
-        ops.rowsum(dz1, B * 4 * P, D, D, 4 * P, G(pre + "token_mix_seq.lin1.bias"))    # db1
         w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                   # [4P, P]
         ops.gemm(eng, P, D, 4 * P, B, w1, MAJOR_MN, ld1, 0, dz1, MAJOR_MN, D, 4 * P * D, dtmp, D, P * D)  # dU = W1^T dZ1
         # dX = dY + LN1bwd(dU); column sums of dX are db4 of the previous block

@@ -54,6 +54,7 @@ int mc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *     x = act(x)                  ; GELU, or x * GELU'(zin[m,n])
  *     x = x + R_b[m,n]            ; optional fp32 residual
  *     C_b[m',n] (=, += or atomic+=) x        with m' = m (+ m / row_remap + 1 if row_remap > 0)
+ *     rowsum_out[m] += sum_{b,n} x           (optional)
  * Replaces the cuBLAS/ATen call sites k1, k4-k11, k16 of SURVEY.md 2.4:
  *   nn.Linear lin1..lin4 + QuickGELU + residual   training/clip/model.py:206-222
  *   patch convolution as an im2col GEMM           training/clip/model.py:258,272
@@ -91,6 +92,9 @@ typedef struct mc_gemm_params {
     int32_t act;
     const float* R;
     int64_t ldr, r_batch_stride;
+    /* optional fused reduction: rowsum_out[m] += sum_{batch, n} of the value written to C (before rounding);
+     * the bias gradient of token-mixing lin1 rides on the dZ1 GEMM this way (model.py:207) */
+    float* rowsum_out;
 } mc_gemm_params;
 
 /* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory; zout / zin fp16. */

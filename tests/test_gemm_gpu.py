@@ -42,9 +42,13 @@ def _gelu_grad(z):
     return s * (1 + 1.702 * z * (1 - s))
 
 
+def scale_hint(K, batch, k_spans):
+    return math.sqrt(K * (batch if k_spans else 1)) + 1.0
+
+
 def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_shared=False, k_spans=False,
              c_bf16=False, bias_mode=0, act=0, zout=False, residual=False, accumulate=False, split_k=1,
-             row_remap=0, pad_a=0, pad_b=0, seed=0):
+             row_remap=0, pad_a=0, pad_b=0, seed=0, rowsum=False):
     ops = _ops()
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -105,11 +109,16 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
         torch.full((ob, Mout, N), 7.0, device=dev, dtype=cdt)
     Cm = C0.clone()
     Z = torch.full((ob, Mout, N), 7.0, device=dev, dtype=zdt) if zout else None
+    rs = torch.full((M,), 3.0, device=dev) if rowsum else None
     ops.gemm(engine, M, N, K, batch, A_mem, a_major, lda, a_bs, B_mem, b_major, ldb, b_bs, Cm, N, Mout * N,
              k_spans_batch=k_spans, accumulate=accumulate, split_k=split_k, row_remap=row_remap, bias=bias,
              bias_mode=bias_mode, zout=Z, ldz=N, z_bs=Mout * N, zin=zin, ldzin=N, zin_bs=Mout * N, act=act, R=R,
-             ldr=N, r_bs=Mout * N)
+             ldr=N, r_bs=Mout * N, rowsum_out=rs)
     torch.cuda.synchronize()
+    if rowsum:
+        exp_rs = 3.0 + x.sum(dim=(0, 2))
+        rerr = ((rs.double() - exp_rs).abs().max() / (scale_hint(K, batch, k_spans) * math.sqrt(N * x.shape[0]))).item()
+        assert rerr <= (3e-3 if engine == "tc" else 2e-5), f"rowsum mismatch {rerr:.3e}"
     expected = place(x, torch.float64, fill=7.0)
     if accumulate or split_k > 1:
         expected = C0.double() + place(x, torch.float64, fill=0.0)
@@ -197,6 +206,16 @@ def test_gemm_token_mix_lin2(engine):
 def test_gemm_token_mix_dgrad(engine):
     # dZ1[b] = (W2^T @ dY[b]) * g'(Z1[b]): A is the MN-major view of W2 [P, 4P]
     run_case(engine, 200, 256, 50, batch=4, a_shared=True, a_major=1, b_major=1, act=2, c_bf16=(engine == "tc"))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_token_mix_dgrad_fused_bias_grad(engine):
+    # db1[h] += sum_{b,d} dZ1[b,h,d] rides on the dZ1 GEMM (rowsum_out); 2 and 3 m-tiles, ragged N
+    run_case(engine, 200, 256, 50, batch=4, a_shared=True, a_major=1, b_major=1, act=2, c_bf16=(engine == "tc"), rowsum=True)
+    run_case(engine, 308, 200, 77, batch=3, a_shared=True, a_major=1, b_major=1, act=2, c_bf16=(engine == "tc"), rowsum=True,
+             pad_a=4)
+    run_case(engine, 788, 96, 197, batch=2, a_shared=True, a_major=1, b_major=1, act=2, c_bf16=(engine == "tc"), rowsum=True,
+             pad_a=4)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
