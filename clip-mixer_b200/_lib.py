@@ -33,7 +33,7 @@ class GemmParams(C.Structure):
         ("zin", C.c_void_p), ("ldzin", C.c_int64), ("zin_batch_stride", C.c_int64),
         ("act", C.c_int32),
         ("R", C.c_void_p), ("ldr", C.c_int64), ("r_batch_stride", C.c_int64),
-        ("rowsum_out", C.c_void_p),
+        ("rowsum_out", C.c_void_p), ("c_transposed", C.c_int32),
     ]
 
 

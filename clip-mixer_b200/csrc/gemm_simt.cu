@@ -23,6 +23,7 @@ struct SimtArgs {
     int act;
     const float* R; long long ldr, r_bs;
     float* rowsum_out;
+    int c_transposed;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
@@ -89,8 +90,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
             if (g.zout) g.zout[(long long)ob * g.z_bs + crow * g.ldz + n] = x;
             if (g.act == MC_ACT_GELU) x = quick_gelu_precise(x);
             else if (g.act == MC_ACT_GELU_BWD) x *= quick_gelu_grad_precise(g.zin[(long long)ob * g.zin_bs + crow * g.ldzin + n]);
-            if (g.R) x += g.R[(long long)ob * g.r_bs + crow * g.ldr + n];
-            float* cp = g.C + (long long)ob * g.c_bs + crow * g.ldc + n;
+            if (g.R) x += g.c_transposed ? g.R[(long long)ob * g.r_bs + (long long)n * g.ldr + crow]
+                                         : g.R[(long long)ob * g.r_bs + crow * g.ldr + n];
+            float* cp = g.c_transposed ? g.C + (long long)ob * g.c_bs + (long long)n * g.ldc + crow
+                                       : g.C + (long long)ob * g.c_bs + crow * g.ldc + n;
             *cp = g.accumulate ? *cp + x : x;
             rsum += x;
         }
@@ -127,6 +130,9 @@ extern "C" int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream_) {
     g.zin = reinterpret_cast<const float*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
     g.rowsum_out = p->rowsum_out;
+    g.c_transposed = p->c_transposed ? 1 : 0;
+    MC_CHECK(!p->c_transposed || (p->zout == nullptr && p->zin == nullptr && p->row_remap == 0),
+             "gemm: c_transposed excludes zout / zin / row_remap");
     const long long tiles = ceil_div(p->M, TM) * ceil_div(p->N, TN);
     MC_CHECK(tiles < (1ll << 31) && g.out_batch < 65536, "simt gemm: grid too large");
     dim3 grid((unsigned)tiles, (unsigned)g.out_batch, 1);

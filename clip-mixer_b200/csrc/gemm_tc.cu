@@ -69,6 +69,7 @@ struct GemmTcArgs {
     const float* R;
     long long ldr, r_bs;
     float* rowsum_out;   // optional: rowsum_out[m] += sum over (batch, n) of the stored value
+    int c_transposed;    // C / R element (m, n) at n*ld + m
 };
 
 struct TileCoord {
@@ -239,7 +240,7 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
     return r;
 }
 
-enum { EPI_GENERIC = 0, EPI_ACT_FWD = 1, EPI_RESID = 2, EPI_ACT_BWD = 3, EPI_PLAIN = 4 };
+enum { EPI_GENERIC = 0, EPI_ACT_FWD = 1, EPI_RESID = 2, EPI_ACT_BWD = 3, EPI_PLAIN = 4, EPI_TRANS = 5 };
 
 // QuickGELU on the tanh unit: x*sigmoid(1.702x) = hx + hx*tanh(0.851x), hx = x/2
 __device__ __forceinline__ float gelu_t(float x) {
@@ -392,6 +393,34 @@ __device__ __forceinline__ void chunk32(const GemmTcArgs& g, uint32_t taddr, flo
                 }
                 stg256f(cp + 8 * j, o);
             }
+        }
+    }
+}
+
+// Transposed fp32 output (D-as-M token-mixing GEMMs): the thread owns row m, so for every column the 32 lanes of
+// the warp touch 32 consecutive addresses - each residual load and each store is one coalesced 128-byte line.
+__device__ __forceinline__ void chunk32_trans(const GemmTcArgs& g, uint32_t taddr, float bias_m, int m, bool row_ok, int b,
+                                              int n) {
+    uint32_t v[32];
+    float r[32];
+    const int ncols = g.N - n < 32 ? g.N - n : 32;
+    if (g.R != nullptr && row_ok) {
+        const float* rp = g.R + (long long)b * g.r_bs + (long long)n * g.ldr + m;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = j < ncols ? rp[(long long)j * g.ldr] : 0.f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0.f;
+    }
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+    if (!row_ok) return;
+    float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + (long long)n * g.ldc + m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < ncols) {
+            const float bb = g.bias_mode == MC_BIAS_N ? g.bias[n + j] : bias_m;
+            cp[(long long)j * g.ldc] = __uint_as_float(v[j]) + bb + r[j];
         }
     }
 }
@@ -847,7 +876,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int nb = n0 + c;
                 if (nb >= g.N) break;  // warp-uniform
                 const int rem = g.N - nb;
-                if (EPI != EPI_GENERIC && g.tma_epi) {
+                if (EPI == EPI_TRANS) {
+                    chunk32_trans(g, t_row + c, bias_m, m, row_ok, tc.b, nb);
+                } else if (EPI != EPI_GENERIC && g.tma_epi) {
                     const int next_n = (c + kChunkStride < g.BN && nb + kChunkStride < g.N) ? nb + kChunkStride : -1;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
                                         nb, lane, zbar, zphase, next_n, rsum);
@@ -1119,14 +1150,20 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         epi = EPI_RESID;
     else if (p->act == MC_ACT_NONE && !c_bf16 && p->R == nullptr && p->zout == nullptr && p->bias_mode == MC_BIAS_NONE)
         epi = EPI_PLAIN;
+    if (p->c_transposed) {
+        MC_CHECK(p->act == MC_ACT_NONE && !c_bf16 && p->zout == nullptr && !p->accumulate && !atomic && p->row_remap == 0 &&
+                     p->rowsum_out == nullptr,
+                 "gemm: c_transposed supports plain fp32 stores with optional bias / residual only");
+        epi = EPI_TRANS;
+    }
     static const int force_generic = env_int("MC_GEMM_GENERIC_EPI", 0);
     static const int allow_tma_epi = env_int("MC_GEMM_TMA_EPI", 1);
-    if (force_generic) epi = EPI_GENERIC;
+    if (force_generic && epi != EPI_TRANS) epi = EPI_GENERIC;
     // TMA stores need 16-byte aligned bases / pitches and no row remapping
     auto al16 = [](const void* q, long long ld, long long bs, int esz) {
         return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 16 == 0) && (ld * esz) % 16 == 0 && (bs * esz) % 16 == 0);
     };
-    g.tma_epi = allow_tma_epi && epi != EPI_GENERIC && p->row_remap == 0 && al16(p->R, p->ldr, p->r_batch_stride, 4) &&
+    g.tma_epi = allow_tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && p->row_remap == 0 && al16(p->R, p->ldr, p->r_batch_stride, 4) &&
                 al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2) &&
                 al16(p->zin, p->ldzin, p->zin_batch_stride, 2);
     const int epi_bytes = g.tma_epi ? kEpiWarps * (int)kEpiWarpBytes : 0;
@@ -1145,6 +1182,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.zin = reinterpret_cast<const __half*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
     g.rowsum_out = p->rowsum_out;
+    g.c_transposed = p->c_transposed ? 1 : 0;
     MC_CHECK(p->rowsum_out == nullptr || epi == EPI_ACT_BWD || epi == EPI_GENERIC,
              "gemm: rowsum_out is supported with the GELU-backward and generic epilogues only");
     MC_CHECK(p->rowsum_out == nullptr || (p->row_remap == 0 && !g.k_spans_batch), "gemm: rowsum_out with row_remap / k_spans_batch");
@@ -1185,7 +1223,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         }
     }
     // the direct (non-TMA) specialised paths use 256-bit accesses and need 32-byte aligned rows
-    if (!g.tma_epi && epi != EPI_GENERIC && !(g.vec_ok && p->row_remap >= 0)) epi = EPI_GENERIC;
+    if (!g.tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && !(g.vec_ok && p->row_remap >= 0)) epi = EPI_GENERIC;
 
     const int slots = sms / g.cluster;
     const int grid = (g.num_tiles < slots ? g.num_tiles : slots) * g.cluster;
@@ -1200,6 +1238,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
         case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
         case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        case EPI_TRANS: return launch_gemm<EPI_TRANS>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
         default: return launch_gemm<EPI_GENERIC>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
     }
 }

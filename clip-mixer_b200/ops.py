@@ -95,7 +95,7 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
          zout: Optional[torch.Tensor] = None, ldz: int = 0, z_bs: int = 0,
          zin: Optional[torch.Tensor] = None, ldzin: int = 0, zin_bs: int = 0,
          act: int = ACT_NONE, R: Optional[torch.Tensor] = None, ldr: int = 0, r_bs: int = 0,
-         rowsum_out: Optional[torch.Tensor] = None):
+         rowsum_out: Optional[torch.Tensor] = None, c_transposed: bool = False):
     """acc[m,n] = sum_k A[b][m,k] B[b][n,k] with the fused epilogue of mc_gemm_params.
 
     engine "tc"   -> mc_gemm_bf16_tc  (A, B, zout, zin bf16)
@@ -123,6 +123,7 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
     p.act = act
     p.R, p.ldr, p.r_batch_stride = _ptr(R), ldr, r_bs
     p.rowsum_out = _ptr(rowsum_out)
+    p.c_transposed = 1 if c_transposed else 0
     fn = lib.mc_gemm_bf16_tc if engine == "tc" else lib.mc_gemm_f32_simt
     if _gemm_timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

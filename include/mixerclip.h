@@ -95,6 +95,11 @@ typedef struct mc_gemm_params {
     /* optional fused reduction: rowsum_out[m] += sum_{batch, n} of the value written to C (before rounding);
      * the bias gradient of token-mixing lin1 rides on the dZ1 GEMM this way (model.py:207) */
     float* rowsum_out;
+    /* != 0: C and R are stored TRANSPOSED: element (m, n) of batch b lives at b*batch_stride + n*ld + m (fp32 C only).
+     * Lets a GEMM whose result is a [P x D] slab run with D as its M dimension (full 128-row tiles, coalesced
+     * 128-byte stores).  Measured slower than the [P x D]-row orientation for the token-mixing shapes in round 1
+     * (profiles/r1g), so the engine does not use it by default; kept as an option of the ABI. */
+    int32_t c_transposed;
 } mc_gemm_params;
 
 /* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory; zout / zin fp16. */

@@ -48,7 +48,7 @@ def scale_hint(K, batch, k_spans):
 
 def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_shared=False, k_spans=False,
              c_bf16=False, bias_mode=0, act=0, zout=False, residual=False, accumulate=False, split_k=1,
-             row_remap=0, pad_a=0, pad_b=0, seed=0, rowsum=False):
+             row_remap=0, pad_a=0, pad_b=0, seed=0, rowsum=False, c_trans=False):
     ops = _ops()
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -110,6 +110,15 @@ def run_case(engine, M, N, K, batch=1, a_major=0, b_major=0, a_shared=False, b_s
     Cm = C0.clone()
     Z = torch.full((ob, Mout, N), 7.0, device=dev, dtype=zdt) if zout else None
     rs = torch.full((M,), 3.0, device=dev) if rowsum else None
+    if c_trans:   # C and R live as [ob, N, M] in memory
+        Ct = torch.full((ob, N, M), 7.0, device=dev)
+        Rt = R.transpose(1, 2).contiguous() if R is not None else None
+        ops.gemm(engine, M, N, K, batch, A_mem, a_major, lda, a_bs, B_mem, b_major, ldb, b_bs, Ct, M, N * M, bias=bias,
+                 bias_mode=bias_mode, R=Rt, ldr=M, r_bs=N * M, c_transposed=True)
+        torch.cuda.synchronize()
+        err = ((Ct.transpose(1, 2).double() - x).abs().max() / scale_hint(K, batch, k_spans)).item()
+        assert err <= (2e-4 if engine == "tc" else 2e-5), f"transposed C mismatch {err:.3e}"
+        return
     ops.gemm(engine, M, N, K, batch, A_mem, a_major, lda, a_bs, B_mem, b_major, ldb, b_bs, Cm, N, Mout * N,
              k_spans_batch=k_spans, accumulate=accumulate, split_k=split_k, row_remap=row_remap, bias=bias,
              bias_mode=bias_mode, zout=Z, ldz=N, z_bs=Mout * N, zin=zin, ldzin=N, zin_bs=Mout * N, act=act, R=R,
@@ -216,6 +225,15 @@ def test_gemm_token_mix_dgrad_fused_bias_grad(engine):
              pad_a=4)
     run_case(engine, 788, 96, 197, batch=2, a_shared=True, a_major=1, b_major=1, act=2, c_bf16=(engine == "tc"), rowsum=True,
              pad_a=4)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_token_mix_d_as_m(engine):
+    # lin2 with D as M: out[d, p] = sum_h H1[h, d] W2[p, h] + b2[p] + x[p, d], stored transposed ([P, D] slab)
+    run_case(engine, 768, 50, 200, batch=5, a_major=1, b_shared=True, bias_mode=1, residual=True, c_trans=True)
+    run_case(engine, 512, 77, 308, batch=3, a_major=1, b_shared=True, bias_mode=1, residual=True, c_trans=True, pad_b=4)
+    # dU = W1^T dZ1 with D as M: both operands MN-major, plain transposed store; ragged D
+    run_case(engine, 200, 17, 68, batch=4, a_major=1, b_major=1, b_shared=True, c_trans=True, pad_b=7)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
