@@ -34,6 +34,9 @@ class GemmParams(C.Structure):
         ("act", C.c_int32),
         ("R", C.c_void_p), ("ldr", C.c_int64), ("r_batch_stride", C.c_int64),
         ("rowsum_out", C.c_void_p), ("c_transposed", C.c_int32),
+        ("A2", C.c_void_p), ("a2_major", C.c_int32), ("lda2", C.c_int64), ("a2_batch_stride", C.c_int64),
+        ("B2", C.c_void_p), ("b2_major", C.c_int32), ("ldb2", C.c_int64), ("b2_batch_stride", C.c_int64),
+        ("bias2", C.c_void_p),
     ]
 
 

@@ -70,6 +70,9 @@ struct GemmTcArgs {
     long long ldr, r_bs;
     float* rowsum_out;   // optional: rowsum_out[m] += sum over (batch, n) of the stored value
     int c_transposed;    // C / R element (m, n) at n*ld + m
+    // second operand pair (recompute of the pre-activation): acc2 lands 128 TMEM columns after acc
+    int dual, a2_mn, b2_mn, a2_batched, b2_batched, pair_bytes;
+    const float* bias2;
 };
 
 struct TileCoord {
@@ -240,7 +243,8 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
     return r;
 }
 
-enum { EPI_GENERIC = 0, EPI_ACT_FWD = 1, EPI_RESID = 2, EPI_ACT_BWD = 3, EPI_PLAIN = 4, EPI_TRANS = 5 };
+enum { EPI_GENERIC = 0, EPI_ACT_FWD = 1, EPI_RESID = 2, EPI_ACT_BWD = 3, EPI_PLAIN = 4, EPI_TRANS = 5, EPI_ACT_BWD_DUAL = 6 };
+constexpr int kDualAccOffset = 128;  // TMEM columns between acc and acc2 (dual mode: BN <= 128)
 
 // QuickGELU on the tanh unit: x*sigmoid(1.702x) = hx + hx*tanh(0.851x), hx = x/2
 __device__ __forceinline__ float gelu_t(float x) {
@@ -458,7 +462,35 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
                                                int next_n, float& rsum) {
     uint32_t v[32];
     [[maybe_unused]] const bool full = n + 32 <= g.N;
-    if constexpr (EPI == EPI_ACT_BWD) {
+    if constexpr (EPI == EPI_ACT_BWD_DUAL) {
+        // the pre-activation is RECOMPUTED by a second GEMM of the same tile (acc2, 128 TMEM columns further):
+        // z = acc2 + bias2[m]; nothing is read from memory for it
+        uint32_t w[32];
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + kDualAccOffset, w);
+        tmem_ld_wait();
+        const float2 b2 = make_float2(bias_m, bias_m);     // bias_m carries bias2[m] in this mode
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 z = __fadd2_rn(make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1])), b2);
+            const float2 r = __fmul2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), gelu_grad2(z));
+            o[i] = pack_bf16x2(r.x, r.y);
+            if (full) rsum += r.x + r.y;
+            else rsum += (n + 2 * i < g.N ? r.x : 0.f) + (n + 2 * i + 1 < g.N ? r.y : 0.f);
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(tmC, stage, n, m_base, b);
+            bulk_commit();
+        }
+    } else if constexpr (EPI == EPI_ACT_BWD) {
         // The saved pre-activation chunk (fp16 [32 x 32], swizzle-64B) was requested by TMA one chunk ahead into
         // the second half of the staging tile (see the epilogue loop); rows >= M / columns >= N arrive as zeros.
         mbar_wait(zbar, zphase);
@@ -671,7 +703,8 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
 template <int EPI, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTcArgs g) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmTcArgs g) {
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -770,12 +803,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         continue;
                     }
-                    mbar_arrive_expect_tx(bar, kABytes + g.b_tx_bytes);
+                    mbar_arrive_expect_tx(bar, (g.dual ? 2u : 1u) * (kABytes + g.b_tx_bytes));
                     if (g.a_mn) {
                         tma_load_3d(a_dst, &tmA, bar, m0, kk, ba);
                         tma_load_3d(a_dst + kGroupBytes, &tmA, bar, m0 + 64, kk, ba);
                     } else {
                         tma_load_3d(a_dst, &tmA, bar, kk, m0, ba);
+                    }
+                    if (g.dual) {   // second operand pair of the same tile (single-CTA mode only)
+                        const uint32_t a2_dst = a_dst + g.pair_bytes, b2_dst = a2_dst + kABytes;
+                        const int ba2 = g.a2_batched ? bb : 0, bb2 = g.b2_batched ? bb : 0;
+                        if (g.a2_mn) {
+                            tma_load_3d(a2_dst, &tmA2, bar, m0, kk, ba2);
+                            tma_load_3d(a2_dst + kGroupBytes, &tmA2, bar, m0 + 64, kk, ba2);
+                        } else {
+                            tma_load_3d(a2_dst, &tmA2, bar, kk, m0, ba2);
+                        }
+                        if (g.b2_mn) {
+                            for (int j = 0; j * 64 < g.BN; ++j)
+                                tma_load_3d(b2_dst + j * kGroupBytes, &tmB2, bar, n0 + j * 64, kk, bb2);
+                        } else {
+                            tma_load_3d(b2_dst, &tmB2, bar, kk, n0, bb2);
+                        }
                     }
                     if (csize == 1) {
                         if (g.b_mn) {
@@ -828,6 +877,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if constexpr (TWO) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
                         else umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
                     }
+                    if (!TWO && g.dual) {
+                        const uint32_t a2_base = a_base + g.pair_bytes, b2_base = a2_base + kABytes;
+                        const uint32_t idesc2 = make_idesc_bf16(BM, g.BN, g.a2_mn, g.b2_mn);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t ad = make_sdesc_sw128(a2_base + k * (g.a2_mn ? 2048u : 32u), g.a2_mn ? kGroupBytes : 16u, 1024u);
+                            const uint64_t bd = make_sdesc_sw128(b2_base + k * (g.b2_mn ? 2048u : 32u), g.b2_mn ? kGroupBytes : 16u, 1024u);
+                            umma_ss(d_tmem + kDualAccOffset, ad, bd, idesc2, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        }
+                    }
                     // the stage is shared through multicast / the pair: release it in every CTA of the cluster
                     if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&empty_bar[stage]), mc_mask);
                     else if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
@@ -859,6 +918,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long crow = g.row_remap > 0 ? (long long)m + m / g.row_remap + 1 : (long long)m;
             float bias_m = 0.f;
             if (g.bias_mode == MC_BIAS_M && row_ok) bias_m = g.bias[m];
+            if (EPI == EPI_ACT_BWD_DUAL && g.bias2 != nullptr && row_ok) bias_m = g.bias2[m];
             const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
             const uint32_t zbar = smem_u32(&zin_bar[e]);
             if ((EPI == EPI_ACT_BWD || EPI == EPI_RESID) && g.tma_epi && lane == 0 && half * 32 < g.BN &&
@@ -1032,7 +1092,8 @@ int make_store_map(CUtensorMap* map, void* ptr, CUtensorMapDataType dt, int esz,
 
 template <int EPI, bool TWO>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmZ,
-                const GemmTcArgs& g, int grid, size_t smem, cudaStream_t stream) {
+                  const CUtensorMap& tmA2, const CUtensorMap& tmB2, const GemmTcArgs& g, int grid, size_t smem,
+                  cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         MC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -1050,15 +1111,16 @@ int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, TWO>, tmA, tmB, tmC, tmZ, g));
+    MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, TWO>, tmA, tmB, tmC, tmZ, tmA2, tmB2, g));
     return MC_OK;
 }
 
 template <int EPI>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmZ,
-                const GemmTcArgs& g, int grid, size_t smem, cudaStream_t stream) {
-    return g.two_cta ? launch_gemm_t<EPI, true>(tmA, tmB, tmC, tmZ, g, grid, smem, stream)
-                     : launch_gemm_t<EPI, false>(tmA, tmB, tmC, tmZ, g, grid, smem, stream);
+                const CUtensorMap& tmA2, const CUtensorMap& tmB2, const GemmTcArgs& g, int grid, size_t smem,
+                cudaStream_t stream) {
+    return g.two_cta ? launch_gemm_t<EPI, true>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem, stream)
+                     : launch_gemm_t<EPI, false>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem, stream);
 }
 
 }  // namespace
@@ -1076,7 +1138,12 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     MC_CHECK(p->A && p->B && p->C, "gemm: null operand");
     MC_CHECK(p->c_dtype == MC_F32 || p->c_dtype == MC_BF16, "gemm: bad c_dtype");
     MC_CHECK(!(p->accumulate && p->c_dtype != MC_F32), "gemm: accumulate needs fp32 C");
-    MC_CHECK(p->act != MC_ACT_GELU_BWD || p->zin != nullptr, "gemm: GELU_BWD needs zin");
+    const bool dual = p->A2 != nullptr;
+    MC_CHECK(p->act != MC_ACT_GELU_BWD || p->zin != nullptr || dual, "gemm: GELU_BWD needs zin (or the A2/B2 recompute pair)");
+    MC_CHECK(!dual || (p->B2 != nullptr && p->act == MC_ACT_GELU_BWD && p->zin == nullptr && p->c_dtype == MC_BF16 &&
+                       !p->k_spans_batch && !p->accumulate && p->row_remap == 0 && p->R == nullptr && p->zout == nullptr &&
+                       p->bias_mode == MC_BIAS_NONE),
+             "gemm: the A2/B2 pair is for C(bf16) = acc * QuickGELU'(acc2 + bias2[m]) only");
     MC_CHECK(p->bias_mode == MC_BIAS_NONE || p->bias != nullptr, "gemm: bias_mode set without bias");
 
     GemmTcArgs g{};
@@ -1099,8 +1166,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     int best_bn = 0, best_split = 1, best_cluster = 1;
     double best = 1e300;
     const int n_cap = (int)(ceil_div(p->N, 32) * 32);
-    for (int cl = 1; cl <= (allow_cluster && tiles_m_all >= 2 ? 2 : 1); ++cl) {
-        for (int bn = 256; bn >= 32; bn -= 32) {
+    for (int cl = 1; cl <= (allow_cluster && tiles_m_all >= 2 && !dual ? 2 : 1); ++cl) {
+        for (int bn = dual ? 128 : 256; bn >= 32; bn -= 32) {
             if (bn > n_cap && bn != 32) continue;
             if (cl == 2 && g.b_mn && bn % 128 != 0 && allow_2cta_sel) continue;   // pair mode needs whole 64-column groups per CTA
             int max_split = 1;
@@ -1117,9 +1184,9 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     // tuning / debugging overrides (read on every call; used by tools/gemm_bench.py sweeps)
     {
         const int f_bn = env_int("MC_GEMM_BN", 0), f_sp = env_int("MC_GEMM_SPLIT", 0), f_cl = env_int("MC_GEMM_CL", 0);
-        if (f_bn > 0 && f_bn <= 256 && f_bn % 32 == 0) best_bn = f_bn;
+        if (f_bn > 0 && f_bn <= (dual ? 128 : 256) && f_bn % 32 == 0) best_bn = f_bn;
         if (f_sp > 0 && (f_sp == 1 || linear_epi) && f_sp <= g.kb_total) best_split = f_sp;
-        if (f_cl == 1 || (f_cl == 2 && tiles_m_all >= 2)) best_cluster = f_cl;
+        if (f_cl == 1 || (f_cl == 2 && tiles_m_all >= 2 && !dual)) best_cluster = f_cl;
     }
     MC_CHECK(best_bn > 0, "gemm: no tile configuration");
     if (best_split > 1) MC_CHECK(linear_epi || p->split_k > 1, "gemm: split-K needs a linear fp32 accumulate epilogue");
@@ -1138,7 +1205,12 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
     const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;
     g.b_tx_bytes = g.b_mn ? (int)(ceil_div(bn_cta, 64) * kGroupBytes) : bn_cta * BK * 2;
-    g.stage_bytes = (int)(kABytes + ceil_div(g.b_tx_bytes, 1024) * 1024);
+    g.pair_bytes = (int)(kABytes + ceil_div(g.b_tx_bytes, 1024) * 1024);
+    g.stage_bytes = g.pair_bytes * (dual ? 2 : 1);
+    g.dual = dual ? 1 : 0;
+    g.a2_mn = p->a2_major == MC_MAJOR_MN; g.b2_mn = p->b2_major == MC_MAJOR_MN;
+    g.a2_batched = (p->a2_batch_stride != 0 && p->batch > 1); g.b2_batched = (p->b2_batch_stride != 0 && p->batch > 1);
+    g.bias2 = p->bias2;
     // epilogue kind: decided before the smem split because the TMA-store epilogues need a staging area
     const bool c_bf16 = p->c_dtype == MC_BF16;
     const bool atomic = best_split > 1;
@@ -1150,6 +1222,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         epi = EPI_RESID;
     else if (p->act == MC_ACT_NONE && !c_bf16 && p->R == nullptr && p->zout == nullptr && p->bias_mode == MC_BIAS_NONE)
         epi = EPI_PLAIN;
+    if (dual) epi = EPI_ACT_BWD_DUAL;
     if (p->c_transposed) {
         MC_CHECK(p->act == MC_ACT_NONE && !c_bf16 && p->zout == nullptr && !p->accumulate && !atomic && p->row_remap == 0 &&
                      p->rowsum_out == nullptr,
@@ -1158,7 +1231,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     }
     static const int force_generic = env_int("MC_GEMM_GENERIC_EPI", 0);
     static const int allow_tma_epi = env_int("MC_GEMM_TMA_EPI", 1);
-    if (force_generic && epi != EPI_TRANS) epi = EPI_GENERIC;
+    if (force_generic && epi != EPI_TRANS && epi != EPI_ACT_BWD_DUAL) epi = EPI_GENERIC;
     // TMA stores need 16-byte aligned bases / pitches and no row remapping
     auto al16 = [](const void* q, long long ld, long long bs, int esz) {
         return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % 16 == 0) && (ld * esz) % 16 == 0 && (bs * esz) % 16 == 0);
@@ -1183,7 +1256,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
     g.rowsum_out = p->rowsum_out;
     g.c_transposed = p->c_transposed ? 1 : 0;
-    MC_CHECK(p->rowsum_out == nullptr || epi == EPI_ACT_BWD || epi == EPI_GENERIC,
+    MC_CHECK(p->rowsum_out == nullptr || epi == EPI_ACT_BWD || epi == EPI_ACT_BWD_DUAL || epi == EPI_GENERIC,
              "gemm: rowsum_out is supported with the GELU-backward and generic epilogues only");
     MC_CHECK(p->rowsum_out == nullptr || (p->row_remap == 0 && !g.k_spans_batch), "gemm: rowsum_out with row_remap / k_spans_batch");
     // vector (8-column) epilogue accesses need every touched row start to be 32-byte aligned
@@ -1200,9 +1273,18 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     rc = make_operand_map(&tmB, p->B, p->b_major, p->N, p->K, p->ldb, p->batch, p->b_batch_stride, g.b_box_rows, "B");
     if (rc != MC_OK) return rc;
 
-    CUtensorMap tmC, tmZ;
+    CUtensorMap tmC, tmZ, tmA2, tmB2;
     memset(&tmC, 0, sizeof(tmC));
     memset(&tmZ, 0, sizeof(tmZ));
+    memset(&tmA2, 0, sizeof(tmA2));
+    memset(&tmB2, 0, sizeof(tmB2));
+    if (dual) {
+        MC_CHECK(g.tma_epi, "gemm: the recompute pair needs 16-byte aligned C rows (TMA-store epilogue)");
+        rc = make_operand_map(&tmA2, p->A2, p->a2_major, p->M, p->K, p->lda2, p->batch, p->a2_batch_stride, BM, "A2");
+        if (rc != MC_OK) return rc;
+        rc = make_operand_map(&tmB2, p->B2, p->b2_major, p->N, p->K, p->ldb2, p->batch, p->b2_batch_stride, g.b_box_rows, "B2");
+        if (rc != MC_OK) return rc;
+    }
     if (g.tma_epi && epi == EPI_RESID) {   // only the residual goes through TMA (loaded); C is stored directly
         rc = make_store_map(&tmZ, const_cast<float*>(p->R), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->N, p->M, g.out_batch, p->ldr,
                             p->r_batch_stride, "R");
@@ -1223,7 +1305,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         }
     }
     // the direct (non-TMA) specialised paths use 256-bit accesses and need 32-byte aligned rows
-    if (!g.tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && !(g.vec_ok && p->row_remap >= 0)) epi = EPI_GENERIC;
+    if (!g.tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && epi != EPI_ACT_BWD_DUAL && !(g.vec_ok && p->row_remap >= 0))
+        epi = EPI_GENERIC;
 
     const int slots = sms / g.cluster;
     const int grid = (g.num_tiles < slots ? g.num_tiles : slots) * g.cluster;
@@ -1234,11 +1317,12 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
                 g.tma_epi, g.num_tiles, grid);
     const size_t smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
     switch (epi) {
-        case EPI_ACT_FWD: return launch_gemm<EPI_ACT_FWD>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
-        case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
-        case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
-        case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
-        case EPI_TRANS: return launch_gemm<EPI_TRANS>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
-        default: return launch_gemm<EPI_GENERIC>(tmA, tmB, tmC, tmZ, g, grid, smem_req, stream);
+        case EPI_ACT_FWD: return launch_gemm<EPI_ACT_FWD>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        case EPI_RESID: return launch_gemm<EPI_RESID>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        case EPI_ACT_BWD: return launch_gemm<EPI_ACT_BWD>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        case EPI_PLAIN: return launch_gemm<EPI_PLAIN>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        case EPI_TRANS: return launch_gemm<EPI_TRANS>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        case EPI_ACT_BWD_DUAL: return launch_gemm_t<EPI_ACT_BWD_DUAL, false>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
+        default: return launch_gemm<EPI_GENERIC>(tmA, tmB, tmC, tmZ, tmA2, tmB2, g, grid, smem_req, stream);
     }
 }

@@ -34,13 +34,16 @@ class Precision:
         # saved pre-activations: fp16 (same bytes as bf16, 8x finer) so that g'(z) in backward adds no
         # rounding noise comparable to an operand rounding
         self.z = torch.float16 if name == "bf16" else torch.float32
+        # tensor-core engine: token-mixing backward recomputes Z1 = W1 U + b1 inside the dZ1 GEMM (second operand
+        # pair), so the forward pass does not store it; the fp32 validation engine keeps the saved copy
+        self.recompute_z1 = name == "bf16"
 
 
 class TowerWS:
     """Per-(tower, batch) activation arena.  With save=False (inference) the per-layer tensors
     collapse to one slot that every layer reuses."""
 
-    def __init__(self, B, P, D, E, L, act, zdt, device, save):
+    def __init__(self, B, P, D, E, L, act, zdt, device, save, keep_z1=True):
         self.B, self.save = B, save
         n = L if save else 1
         f32 = dict(device=device, dtype=torch.float32)
@@ -49,7 +52,7 @@ class TowerWS:
         self.y = torch.empty(n, B, P, D, **f32)                       # mid-block residual
         self.u = torch.empty(n, B, P, D, **a)
         self.v = torch.empty(n, B, P, D, **a)
-        self.z1 = torch.empty(n, B, 4 * P, D, device=device, dtype=zdt) if save else None
+        self.z1 = torch.empty(n, B, 4 * P, D, device=device, dtype=zdt) if (save and keep_z1) else None
         self.h1 = torch.empty(n, B, 4 * P, D, **a)
         self.z2 = torch.empty(n, B * P, 4 * D, device=device, dtype=zdt) if save else None
         self.h2 = torch.empty(n, B * P, 4 * D, **a)
@@ -114,7 +117,8 @@ class TowerRT:
             # keep at most one training and one inference arena per tower
             for k in [k for k in self._ws if k[2] == save]:
                 del self._ws[k]
-            ws = TowerWS(B, self.P, self.D, self.E, self.L, prec.act, prec.z, self.store.device, save)
+            ws = TowerWS(B, self.P, self.D, self.E, self.L, prec.act, prec.z, self.store.device, save,
+                         keep_z1=not prec.recompute_z1)
             self._ws[key] = ws
         return ws
 
@@ -177,7 +181,7 @@ class TowerRT:
         x = ws.x[i] if save else ws.x[i % 2]
         xo = ws.x[i + 1] if save else ws.x[(i + 1) % 2]
         y, u, v, h1, h2, st = ws.y[s], ws.u[s], ws.v[s], ws.h1[s], ws.h2[s], ws.stats[s]
-        z1 = ws.z1[s] if save else None
+        z1 = ws.z1[s] if (save and ws.z1 is not None) else None
         z2 = ws.z2[s] if save else None
         pre = f"{self.blk}.{i}."
         # x + token_mix(LN1(x))                                                          model.py:216,220-222
@@ -260,7 +264,7 @@ class TowerRT:
         sep = prec.act != torch.float32
         dcur, dcur_a, dtmp, dz2, dz1 = s["dcur"], s["dcur_a"], s["dtmp"], s["dz2"], s["dz1"]
         x, y, u, v = ws.x[i], ws.y[i], ws.u[i], ws.v[i]
-        z1, h1, z2, h2, stt = ws.z1[i], ws.h1[i], ws.z2[i], ws.h2[i], ws.stats[i]
+        h1, z2, h2, stt = ws.h1[i], ws.z2[i], ws.h2[i], ws.stats[i]
         pre = f"{self.blk}.{i}."
         T = B * P
         # ---- channel mix:  O = Y + g(V W3^T + b3) W4^T + b4 ----
@@ -282,16 +286,24 @@ class TowerRT:
                    rowsum_out=G(pre + "token_mix_seq.lin2.bias"), rowsum_period=P)
         # ---- token mix:  Y = X + W2 g(W1 U + b1) + b2   (per sample, U = LN1(X)) ----
         w2, ld2 = self.wop(pre + "token_mix_seq.lin2.weight", prec)                   # [P, 4P]
-        ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
-                 act=ACT_GELU_BWD, zin=z1, ldzin=D, zin_bs=4 * P * D,
-                 rowsum_out=G(pre + "token_mix_seq.lin1.bias"))                        # dZ1 = (W2^T dY) * g'(Z1); db1 fused
+        w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                   # [4P, P]
+        if prec.recompute_z1:
+            # dZ1 = (W2^T dY) * g'(W1 U + b1): the pre-activation is recomputed by a second operand pair of the same
+            # GEMM tile (K = P is tiny), nothing was saved for it in the forward pass
+            ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
+                     act=ACT_GELU_BWD, rowsum_out=G(pre + "token_mix_seq.lin1.bias"),
+                     A2=w1, a2_major=MAJOR_K, lda2=ld1, a2_bs=0, B2=u, b2_major=MAJOR_MN, ldb2=D, b2_bs=P * D,
+                     bias2=self.bp(i, "token_mix_seq.lin1.bias"))
+        else:
+            ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
+                     act=ACT_GELU_BWD, zin=ws.z1[i], ldzin=D, zin_bs=4 * P * D,
+                     rowsum_out=G(pre + "token_mix_seq.lin1.bias"))                    # dZ1 = (W2^T dY) * g'(Z1); db1 fused
         g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
         ops.gemm(eng, P, 4 * P, D, B, dcur_a, MAJOR_K, D, P * D, h1, MAJOR_K, D, 4 * P * D, g2, ldg2, 0,
                  k_spans_batch=True, accumulate=True, split_k=0)                       # dW2 += sum_b dY H1^T
         g1, ldg1 = st.grad2d(pre + "token_mix_seq.lin1.weight")
         ops.gemm(eng, 4 * P, P, D, B, dz1, MAJOR_K, D, 4 * P * D, u, MAJOR_K, D, P * D, g1, ldg1, 0,
                  k_spans_batch=True, accumulate=True, split_k=0)                       # dW1 += sum_b dZ1 U^T
-        w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                   # [4P, P]
         ops.gemm(eng, P, D, 4 * P, B, w1, MAJOR_MN, ld1, 0, dz1, MAJOR_MN, D, 4 * P * D, dtmp, D, P * D)  # dU = W1^T dZ1
         # dX = dY + LN1bwd(dU); column sums of dX are db4 of the previous block
         prev_b4 = G(f"{self.blk}.{i - 1}.channel_mix_seq.lin4.bias") if i > 0 else None

@@ -95,7 +95,10 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
          zout: Optional[torch.Tensor] = None, ldz: int = 0, z_bs: int = 0,
          zin: Optional[torch.Tensor] = None, ldzin: int = 0, zin_bs: int = 0,
          act: int = ACT_NONE, R: Optional[torch.Tensor] = None, ldr: int = 0, r_bs: int = 0,
-         rowsum_out: Optional[torch.Tensor] = None, c_transposed: bool = False):
+         rowsum_out: Optional[torch.Tensor] = None, c_transposed: bool = False,
+         A2: Optional[torch.Tensor] = None, a2_major: int = 0, lda2: int = 0, a2_bs: int = 0,
+         B2: Optional[torch.Tensor] = None, b2_major: int = 0, ldb2: int = 0, b2_bs: int = 0,
+         bias2: Optional[torch.Tensor] = None):
     """acc[m,n] = sum_k A[b][m,k] B[b][n,k] with the fused epilogue of mc_gemm_params.
 
     engine "tc"   -> mc_gemm_bf16_tc  (A, B, zout, zin bf16)
@@ -124,6 +127,12 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
     p.R, p.ldr, p.r_batch_stride = _ptr(R), ldr, r_bs
     p.rowsum_out = _ptr(rowsum_out)
     p.c_transposed = 1 if c_transposed else 0
+    for name, t in (("A2", A2), ("B2", B2)):
+        if t is not None and t.dtype != want:
+            raise MixerClipError(f"gemm[{engine}]: operand {name} must be {want}, got {t.dtype}")
+    p.A2, p.a2_major, p.lda2, p.a2_batch_stride = _ptr(A2), a2_major, lda2, a2_bs
+    p.B2, p.b2_major, p.ldb2, p.b2_batch_stride = _ptr(B2), b2_major, ldb2, b2_bs
+    p.bias2 = _ptr(bias2)
     fn = lib.mc_gemm_bf16_tc if engine == "tc" else lib.mc_gemm_f32_simt
     if _gemm_timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -100,6 +100,18 @@ typedef struct mc_gemm_params {
      * 128-byte stores).  Measured slower than the [P x D]-row orientation for the token-mixing shapes in round 1
      * (profiles/r1g), so the engine does not use it by default; kept as an option of the ABI. */
     int32_t c_transposed;
+    /* Optional second operand pair with the same M, N, K, batch (tensor-core engine, act == MC_ACT_GELU_BWD and
+     * zin == NULL): acc2[m,n] = sum_k A2_b[m,k] * B2_b[n,k] is computed next to acc and the epilogue uses
+     * z = acc2 + bias2[m] instead of a saved pre-activation:  C = acc * QuickGELU'(acc2 + bias2[m]).
+     * Token-mixing backward recomputes Z1 = W1 U + b1 this way (K = P is tiny), so the forward pass never stores
+     * Z1 and the backward pass never reads it ("backward must recompute Z1/H1"). */
+    const void* A2;
+    int32_t a2_major;
+    int64_t lda2, a2_batch_stride;
+    const void* B2;
+    int32_t b2_major;
+    int64_t ldb2, b2_batch_stride;
+    const float* bias2;
 } mc_gemm_params;
 
 /* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory; zout / zin fp16. */

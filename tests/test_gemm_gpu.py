@@ -279,3 +279,34 @@ def test_gemm_rejects_bad_args():
         ops.gemm("tc", 16, 16, 50, 1, a, 0, 50, 0, b, 0, 50, 0, c, 16, 0)
     with pytest.raises(MixerClipError):
         ops.gemm("tc", 16, 16, 50, 1, a.float(), 0, 50, 0, b, 0, 50, 0, c, 16, 0)
+
+
+def test_gemm_tc_recompute_pair():
+    """C = (A B^T) * QuickGELU'(A2 B2^T + bias2[m]) with the pre-activation recomputed by a second operand pair
+    (token-mixing dZ1 without a saved Z1), plus the fused row sums; compared with the same math in fp64."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    for (M, N, K, batch, ldw) in ((200, 768, 50, 5, 56), (308, 512, 77, 3, 80), (68, 64, 17, 4, 24)):
+        W2t = torch.randn(K, M, generator=g)                   # A as the MN-major view of W2 [P, 4P]
+        dY = torch.randn(batch, K, N, generator=g)             # B MN-major
+        W1 = torch.randn(M, K, generator=g)                    # A2 K-major, padded pitch
+        U = torch.randn(batch, K, N, generator=g)              # B2 MN-major
+        b1 = torch.randn(M, generator=g)
+        ldm = (M + 7) // 8 * 8
+        A = torch.zeros(K, ldm, dtype=torch.bfloat16, device=dev)
+        A[:, :M] = W2t.to(dev)
+        A2 = torch.zeros(M, ldw, dtype=torch.bfloat16, device=dev)
+        A2[:, :K] = W1.to(dev)
+        Bm, B2 = dY.to(dev).to(torch.bfloat16), U.to(dev).to(torch.bfloat16)
+        C = torch.empty(batch, M, N, device=dev, dtype=torch.bfloat16)
+        rs = torch.zeros(M, device=dev)
+        ops.gemm("tc", M, N, K, batch, A, 1, ldm, 0, Bm, 1, N, K * N, C, N, M * N, act=ops.ACT_GELU_BWD, rowsum_out=rs,
+                 A2=A2, a2_major=0, lda2=ldw, a2_bs=0, B2=B2, b2_major=1, ldb2=N, b2_bs=K * N, bias2=b1.to(dev))
+        torch.cuda.synchronize()
+        acc = torch.einsum("km,bkn->bmn", A[:, :M].double(), Bm.double())
+        z = torch.einsum("mk,bkn->bmn", A2[:, :K].double(), B2.double()) + b1.to(dev).double()[None, :, None]
+        ref = acc * _gelu_grad(z)
+        scale = math.sqrt(K) + 1
+        assert ((C.double() - ref).abs().max() / scale).item() <= 2e-2
+        assert ((rs.double() - ref.sum((0, 2))).abs().max() / (scale * math.sqrt(N * batch))).item() <= 3e-3
