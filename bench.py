@@ -245,8 +245,16 @@ def main():
         ach = fl_tc / t_tc / 1e12 if t_tc > 0 else 0.0
         big = [r for r in tc if r["flops"] > 2e10]
         t_big = sum(r["ms"] for r in big) * 1e-3
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes of the same launch set (one step), from the committed ncu launch list of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_gemm_traffic.json")))
+            if args.model == "B32" and B == 256:
+                traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM engine, all launches of one step)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per step over the same launches", "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches": len(tc), "gemm_ms_per_step": t_tc * 1e3,
                 "algorithmic_gflop_per_step": fl_tc / 1e9,
                 "channel_mix_only": {"achieved": (sum(r["flops"] for r in big) / t_big / 1e12) if t_big else None,
