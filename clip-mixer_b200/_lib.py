@@ -40,6 +40,18 @@ class GemmParams(C.Structure):
     ]
 
 
+class TokenMixParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("P", C.c_int64), ("D", C.c_int64),
+        ("u", C.c_void_p),
+        ("w1", C.c_void_p), ("ld1", C.c_int64), ("b1", C.c_void_p),
+        ("w2", C.c_void_p), ("ld2", C.c_int64), ("b2", C.c_void_p),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p),
+        ("spill", C.c_void_p), ("spill_ld", C.c_int64),
+        ("gw1", C.c_void_p), ("ldg1", C.c_int64), ("gw2", C.c_void_p), ("ldg2", C.c_int64), ("gb1", C.c_void_p),
+    ]
+
+
 _I64, _I32, _F, _P = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 
 # name -> argument types (all return int unless noted); mirrors include/mixerclip.h
@@ -48,6 +60,10 @@ SIGNATURES = {
     "mc_device_info": [_P, _P, _P],
     "mc_gemm_bf16_tc": [C.POINTER(GemmParams), _P],
     "mc_gemm_f32_simt": [C.POINTER(GemmParams), _P],
+    "mc_token_mix_supported": [_I64, _I64],
+    "mc_token_mix_fwd": [C.POINTER(TokenMixParams), _P],
+    "mc_token_mix_dgrad": [C.POINTER(TokenMixParams), _P],
+    "mc_token_mix_wgrad": [C.POINTER(TokenMixParams), _P],
     "mc_ln_fwd": [_P, _I64, _P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _P, _I64, _I64, _P],
     "mc_ln_bwd": [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _I64, _P, _I64,
                   _I64, _P],

@@ -12,6 +12,7 @@ Math follows SURVEY.md Appendix A, which restates training/clip/model.py:215-222
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -20,6 +21,12 @@ from . import ops
 from ._lib import MixerClipError
 from .ops import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BIAS_M, BIAS_N, MAJOR_K, MAJOR_MN)
 from .params import ParamStore
+
+
+def fused_token_mix_enabled() -> bool:
+    """MC_TOKENMIX=gemm selects the unfused token-mixing schedule (separate engine GEMMs with a materialised
+    [B, 4P, D] hidden tensor) for A/B measurements; the default is the fused kernels of csrc/tokenmix.cu."""
+    return os.environ.get("MC_TOKENMIX", "fused") != "gemm"
 
 
 class Precision:
@@ -43,8 +50,8 @@ class TowerWS:
     """Per-(tower, batch) activation arena.  With save=False (inference) the per-layer tensors
     collapse to one slot that every layer reuses."""
 
-    def __init__(self, B, P, D, E, L, act, zdt, device, save, keep_z1=True):
-        self.B, self.save = B, save
+    def __init__(self, B, P, D, E, L, act, zdt, device, save, keep_z1=True, fused_tm=False):
+        self.B, self.save, self.fused_tm = B, save, fused_tm
         n = L if save else 1
         f32 = dict(device=device, dtype=torch.float32)
         a = dict(device=device, dtype=act)
@@ -52,8 +59,9 @@ class TowerWS:
         self.y = torch.empty(n, B, P, D, **f32)                       # mid-block residual
         self.u = torch.empty(n, B, P, D, **a)
         self.v = torch.empty(n, B, P, D, **a)
-        self.z1 = torch.empty(n, B, 4 * P, D, device=device, dtype=zdt) if (save and keep_z1) else None
-        self.h1 = torch.empty(n, B, 4 * P, D, **a)
+        # fused token mixing keeps the hidden activation on chip (forward) and recomputes it (backward)
+        self.z1 = torch.empty(n, B, 4 * P, D, device=device, dtype=zdt) if (save and keep_z1 and not fused_tm) else None
+        self.h1 = torch.empty(n, B, 4 * P, D, **a) if not fused_tm else None
         self.z2 = torch.empty(n, B * P, 4 * D, device=device, dtype=zdt) if save else None
         self.h2 = torch.empty(n, B * P, 4 * D, **a)
         self.stats = torch.empty(n, 4, B * P, **f32)                  # mean1, rstd1, mean2, rstd2
@@ -78,7 +86,7 @@ class TowerWS:
         s["dcur_a"] = torch.empty(B, P, D, **a) if act != torch.float32 else s["dcur"]
         s["dtmp"] = torch.empty(B, P, D, **f32)
         s["dz2"] = torch.empty(B * P, 4 * D, **a)
-        s["dz1"] = torch.empty(B, 4 * P, D, **a)
+        s["dz1"] = torch.empty(B, (1 if self.fused_tm else 4) * P, D, **a)   # fused: only the image tower's operand scratch
         s["dfeat"] = torch.empty(B, E, **f32)
         self.bwd = s
         return s
@@ -111,19 +119,22 @@ class TowerRT:
         return self.store.weight_operand(name, prec.act)
 
     def workspace(self, B, prec: Precision, save: bool) -> TowerWS:
-        key = (B, prec.name, save)
+        key = (B, prec.name, save, self.fused_tm(prec))
         ws = self._ws.get(key)
         if ws is None:
             # keep at most one training and one inference arena per tower
             for k in [k for k in self._ws if k[2] == save]:
                 del self._ws[k]
             ws = TowerWS(B, self.P, self.D, self.E, self.L, prec.act, prec.z, self.store.device, save,
-                         keep_z1=not prec.recompute_z1)
+                         keep_z1=not prec.recompute_z1, fused_tm=self.fused_tm(prec))
             self._ws[key] = ws
         return ws
 
     def release(self):
         self._ws.clear()
+
+    def fused_tm(self, prec: Precision) -> bool:
+        return prec.engine == "tc" and fused_token_mix_enabled() and ops.token_mix_supported(self.P, self.D)
 
     # ---- forward --------------------------------------------------------------------------------
     def forward(self, inp: torch.Tensor, prec: Precision, save: bool) -> TowerWS:
@@ -180,19 +191,25 @@ class TowerRT:
         s = i if save else 0
         x = ws.x[i] if save else ws.x[i % 2]
         xo = ws.x[i + 1] if save else ws.x[(i + 1) % 2]
-        y, u, v, h1, h2, st = ws.y[s], ws.u[s], ws.v[s], ws.h1[s], ws.h2[s], ws.stats[s]
+        y, u, v, h2, st = ws.y[s], ws.u[s], ws.v[s], ws.h2[s], ws.stats[s]
+        h1 = ws.h1[s] if ws.h1 is not None else None
         z1 = ws.z1[s] if (save and ws.z1 is not None) else None
         z2 = ws.z2[s] if save else None
         pre = f"{self.blk}.{i}."
         # x + token_mix(LN1(x))                                                          model.py:216,220-222
         ops.ln_fwd(x, D, self.bp(i, "layerNorm1.weight"), self.bp(i, "layerNorm1.bias"), u, D, st[0], st[1], B * P, D)
         w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                       # [4P, P]
-        ops.gemm(eng, 4 * P, D, P, B, w1, MAJOR_K, ld1, 0, u, MAJOR_MN, D, P * D, h1, D, 4 * P * D,
-                 bias=self.bp(i, "token_mix_seq.lin1.bias"), bias_mode=BIAS_M, zout=z1, ldz=D, z_bs=4 * P * D,
-                 act=ACT_GELU)
         w2, ld2 = self.wop(pre + "token_mix_seq.lin2.weight", prec)                       # [P, 4P]
-        ops.gemm(eng, P, D, 4 * P, B, w2, MAJOR_K, ld2, 0, h1, MAJOR_MN, D, 4 * P * D, y, D, P * D,
-                 bias=self.bp(i, "token_mix_seq.lin2.bias"), bias_mode=BIAS_M, R=x, ldr=D, r_bs=P * D)
+        if ws.fused_tm:
+            # one kernel: both GEMMs, bias, QuickGELU and the residual; the hidden [4P x D] tile never leaves the SM
+            ops.token_mix_fwd(B, P, D, u, x, y, w1, ld1, self.bp(i, "token_mix_seq.lin1.bias"), w2, ld2,
+                              self.bp(i, "token_mix_seq.lin2.bias"))
+        else:
+            ops.gemm(eng, 4 * P, D, P, B, w1, MAJOR_K, ld1, 0, u, MAJOR_MN, D, P * D, h1, D, 4 * P * D,
+                     bias=self.bp(i, "token_mix_seq.lin1.bias"), bias_mode=BIAS_M, zout=z1, ldz=D, z_bs=4 * P * D,
+                     act=ACT_GELU)
+            ops.gemm(eng, P, D, 4 * P, B, w2, MAJOR_K, ld2, 0, h1, MAJOR_MN, D, 4 * P * D, y, D, P * D,
+                     bias=self.bp(i, "token_mix_seq.lin2.bias"), bias_mode=BIAS_M, R=x, ldr=D, r_bs=P * D)
         # y + channel_mix(LN2(y))                                                         model.py:217
         ops.ln_fwd(y, D, self.bp(i, "layerNorm2.weight"), self.bp(i, "layerNorm2.bias"), v, D, st[2], st[3], B * P, D)
         w3, ld3 = self.wop(pre + "channel_mix_seq.lin3.weight", prec)                     # [4D, D]
@@ -264,7 +281,8 @@ class TowerRT:
         sep = prec.act != torch.float32
         dcur, dcur_a, dtmp, dz2, dz1 = s["dcur"], s["dcur_a"], s["dtmp"], s["dz2"], s["dz1"]
         x, y, u, v = ws.x[i], ws.y[i], ws.u[i], ws.v[i]
-        h1, z2, h2, stt = ws.h1[i], ws.z2[i], ws.h2[i], ws.stats[i]
+        z2, h2, stt = ws.z2[i], ws.h2[i], ws.stats[i]
+        h1 = ws.h1[i] if ws.h1 is not None else None
         pre = f"{self.blk}.{i}."
         T = B * P
         # ---- channel mix:  O = Y + g(V W3^T + b3) W4^T + b4 ----
@@ -287,7 +305,15 @@ class TowerRT:
         # ---- token mix:  Y = X + W2 g(W1 U + b1) + b2   (per sample, U = LN1(X)) ----
         w2, ld2 = self.wop(pre + "token_mix_seq.lin2.weight", prec)                   # [P, 4P]
         w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                   # [4P, P]
-        if prec.recompute_z1:
+        if ws.fused_tm:
+            # weight gradients and the data gradient each in one kernel; both recompute Z1 / H1 / dZ1 per tile on chip
+            g1, ldg1 = st.grad2d(pre + "token_mix_seq.lin1.weight")
+            g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
+            b1 = self.bp(i, "token_mix_seq.lin1.bias")
+            ops.token_mix_wgrad(B, P, D, u, dcur_a, w1, ld1, b1, w2, ld2, g1, ldg1, g2, ldg2,
+                                G(pre + "token_mix_seq.lin1.bias"))
+            ops.token_mix_dgrad(B, P, D, u, dcur_a, dtmp, w1, ld1, b1, w2, ld2)
+        elif prec.recompute_z1:
             # dZ1 = (W2^T dY) * g'(W1 U + b1): the pre-activation is recomputed by a second operand pair of the same
             # GEMM tile (K = P is tiny), nothing was saved for it in the forward pass
             ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
@@ -298,13 +324,14 @@ class TowerRT:
             ops.gemm(eng, 4 * P, D, P, B, w2, MAJOR_MN, ld2, 0, dcur_a, MAJOR_MN, D, P * D, dz1, D, 4 * P * D,
                      act=ACT_GELU_BWD, zin=ws.z1[i], ldzin=D, zin_bs=4 * P * D,
                      rowsum_out=G(pre + "token_mix_seq.lin1.bias"))                    # dZ1 = (W2^T dY) * g'(Z1); db1 fused
-        g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
-        ops.gemm(eng, P, 4 * P, D, B, dcur_a, MAJOR_K, D, P * D, h1, MAJOR_K, D, 4 * P * D, g2, ldg2, 0,
-                 k_spans_batch=True, accumulate=True, split_k=0)                       # dW2 += sum_b dY H1^T
-        g1, ldg1 = st.grad2d(pre + "token_mix_seq.lin1.weight")
-        ops.gemm(eng, 4 * P, P, D, B, dz1, MAJOR_K, D, 4 * P * D, u, MAJOR_K, D, P * D, g1, ldg1, 0,
-                 k_spans_batch=True, accumulate=True, split_k=0)                       # dW1 += sum_b dZ1 U^T
-        ops.gemm(eng, P, D, 4 * P, B, w1, MAJOR_MN, ld1, 0, dz1, MAJOR_MN, D, 4 * P * D, dtmp, D, P * D)  # dU = W1^T dZ1
+        if not ws.fused_tm:
+            g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
+            ops.gemm(eng, P, 4 * P, D, B, dcur_a, MAJOR_K, D, P * D, h1, MAJOR_K, D, 4 * P * D, g2, ldg2, 0,
+                     k_spans_batch=True, accumulate=True, split_k=0)                       # dW2 += sum_b dY H1^T
+            g1, ldg1 = st.grad2d(pre + "token_mix_seq.lin1.weight")
+            ops.gemm(eng, 4 * P, P, D, B, dz1, MAJOR_K, D, 4 * P * D, u, MAJOR_K, D, P * D, g1, ldg1, 0,
+                     k_spans_batch=True, accumulate=True, split_k=0)                       # dW1 += sum_b dZ1 U^T
+            ops.gemm(eng, P, D, 4 * P, B, w1, MAJOR_MN, ld1, 0, dz1, MAJOR_MN, D, 4 * P * D, dtmp, D, P * D)  # dU = W1^T dZ1
         # dX = dY + LN1bwd(dU); column sums of dX are db4 of the previous block
         prev_b4 = G(f"{self.blk}.{i - 1}.channel_mix_seq.lin4.bias") if i > 0 else None
         ops.ln_bwd(dtmp, x, D, stt[0], stt[1], self.bp(i, "layerNorm1.weight"), dcur, D, G(pre + "layerNorm1.weight"),

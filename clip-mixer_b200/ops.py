@@ -13,9 +13,9 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_NONE, F32, MAJOR_K, MAJOR_MN,
-                   GemmParams, MixerClipError, check)
+                   GemmParams, MixerClipError, TokenMixParams, check)
 
-__all__ = ["gemm", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
+__all__ = ["gemm", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
            "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "adamw", "device_info",
            "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
            "ACT_GELU_BWD", "launch_count", "reset_launch_count", "enable_gemm_timing", "collect_gemm_timing"]
@@ -143,6 +143,62 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
         tag = f"a{a_major}b{b_major}" + ("kb" if k_spans_batch else "") + (f"act{act}" if act else "")
         _gemm_timing.append((engine, M, N, K, batch, e0, e1, tag))
     _count()
+
+
+def token_mix_supported(P: int, D: int) -> bool:
+    """True when the fused token-mixing kernels (mc_token_mix_*) cover the shape (P <= 80 tokens, D % 128 == 0)."""
+    return bool(_lib.load().mc_token_mix_supported(P, D))
+
+
+def _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2):
+    for name, t in (("u", u), ("w1", w1), ("w2", w2)):
+        if t.dtype != torch.bfloat16:
+            raise MixerClipError(f"token_mix: operand {name} must be bf16, got {t.dtype}")
+    p = TokenMixParams()
+    p.B, p.P, p.D = B, P, D
+    p.u, p.w1, p.ld1, p.b1, p.w2, p.ld2 = _ptr(u), _ptr(w1), ld1, _ptr(b1), _ptr(w2), ld2
+    return p
+
+
+def _tm_call(fn, p, what, B, P, D):
+    if _gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(fn(C.byref(p), _stream()), what)
+    if _gemm_timing is not None:
+        e1.record()
+        # FLOPs executed on the tensor cores: 2 GEMMs (fwd), 3 (dgrad), 4 (wgrad) of 2*4P*P*D per sample
+        n = {"token_mix_fwd": 2, "token_mix_dgrad": 3, "token_mix_wgrad": 4}[what]
+        _gemm_timing.append((what, 4 * P, D, P, B * n, e0, e1, what))
+    _count()
+
+
+def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2, spill=None, spill_ld=0):
+    """y = x + W2 g(W1 u + b1) + b2 per sample (model.py:216,220-222), one fused kernel."""
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p.b2, p.x, p.y, p.spill, p.spill_ld = _ptr(b2), _ptr(x), _ptr(y), _ptr(spill), spill_ld
+    _tm_call(_lib.load().mc_token_mix_fwd, p, "token_mix_fwd", B, P, D)
+
+
+def token_mix_dgrad(B, P, D, u, dy, du, w1, ld1, b1, w2, ld2, spill=None, spill_ld=0):
+    """du = W1^T ((W2^T dy) * g'(W1 u + b1)) per sample, one fused kernel (dy bf16, du fp32)."""
+    if dy.dtype != torch.bfloat16 or du.dtype != torch.float32:
+        raise MixerClipError("token_mix_dgrad: dy must be bf16 and du fp32")
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p.dy, p.y, p.spill, p.spill_ld = _ptr(dy), _ptr(du), _ptr(spill), spill_ld
+    _tm_call(_lib.load().mc_token_mix_dgrad, p, "token_mix_dgrad", B, P, D)
+
+
+def token_mix_wgrad(B, P, D, u, dy, w1, ld1, b1, w2, ld2, gw1, ldg1, gw2, ldg2, gb1):
+    """gw1 += sum_b dZ1 u^T, gw2 += sum_b dy H1^T, gb1 += rowsum(dZ1); H1 and dZ1 are recomputed on chip."""
+    if dy.dtype != torch.bfloat16:
+        raise MixerClipError("token_mix_wgrad: dy must be bf16")
+    for t in (gw1, gw2, gb1):
+        if t.dtype != torch.float32:
+            raise MixerClipError("token_mix_wgrad: gradients must be fp32")
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p.dy, p.gw1, p.ldg1, p.gw2, p.ldg2, p.gb1 = _ptr(dy), _ptr(gw1), ldg1, _ptr(gw2), ldg2, _ptr(gb1)
+    _tm_call(_lib.load().mc_token_mix_wgrad, p, "token_mix_wgrad", B, P, D)
 
 
 def ln_fwd(x, x_row_stride, gamma, beta, y, y_row_stride, mean, rstd, rows, D, *, row_index=None, cls=None,

@@ -120,6 +120,44 @@ int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream);
 int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused token-mixing MLP of one Mixer block (tcgen05 engine only), training/clip/model.py:206-208,216,220-222:
+ *     y = x + ( lin2( QuickGELU( lin1( u.permute(0,2,1) ) ) ) ).permute(0,2,1),      u = LN1(x)  (bf16 [B,P,D])
+ * One persistent kernel per call; the [B, D, 4P] hidden activation never reaches HBM and no transposed copy of
+ * the activation is made (the permute lives in the UMMA descriptor).  Per sample, with W1 [4P x P], W2 [P x 4P]:
+ *   mc_token_mix_fwd    y  = x + W2 g(W1 u + b1) + b2                                  (x, y fp32 [B,P,D], x != y)
+ *   mc_token_mix_dgrad  y  = W1^T ( (W2^T dy) * g'(W1 u + b1) )                         (dy bf16 [B,P,D]; y = dU fp32)
+ *   mc_token_mix_wgrad  gw2 += sum_b dy H1^T, gw1 += sum_b dZ1 u^T, gb1 += rowsum(dZ1)  (H1, dZ1 recomputed on chip)
+ * w1 / w2 are the bf16 operand copies with row pitches ld1 / ld2 (multiples of 8, pad elements ignored).
+ * spill (optional, fwd / dgrad): bf16 [B, D, spill_ld] copy of H1^T (fwd) or dZ1^T (dgrad) for an unfused consumer.
+ * Supported shapes: mc_token_mix_supported(P, D) != 0  (P <= 80 tokens, D a multiple of 128); other shapes
+ * (B/16: 197 tokens) run the same math as separate mc_gemm_bf16_tc calls.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mc_token_mix_params {
+    int64_t B, P, D;
+    const void* u;
+    const void* w1;
+    int64_t ld1;
+    const float* b1;
+    const void* w2;
+    int64_t ld2;
+    const float* b2;
+    const float* x;
+    float* y;
+    const void* dy;
+    void* spill;
+    int64_t spill_ld;
+    float* gw1;
+    int64_t ldg1;
+    float* gw2;
+    int64_t ldg2;
+    float* gb1;
+} mc_token_mix_params;
+int mc_token_mix_supported(int64_t P, int64_t D);
+int mc_token_mix_fwd(const mc_token_mix_params* p, void* stream);
+int mc_token_mix_dgrad(const mc_token_mix_params* p, void* stream);
+int mc_token_mix_wgrad(const mc_token_mix_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * LayerNorm (always fp32 math), training/clip/model.py:166-172; instances ln_pre :263,
  * layerNorm1/2 :205,210, ln_post :268, ln_final :344.
  *   row r reads x + (row_index ? row_index[r] : r) * x_row_stride; rows with
