@@ -583,7 +583,7 @@ int tm_launch(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap
               const TmArgs& g, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
     token_mix_kernel<MODE><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, tmS, g);
@@ -671,7 +671,7 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     if (g.stages > kMaxTmStages) g.stages = kMaxTmStages;
     size_t smem = (size_t)off + (size_t)g.stages * g.stage_bytes + 1024 + slack;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM (each allocates all of TMEM)
-    MC_CHECK(smem <= 227 * 1024, "token_mix: shape does not fit in shared memory");
+    MC_CHECK(smem <= 226 * 1024, "token_mix: shape does not fit in shared memory");
     MC_CHECK(mode != TM_FWD || p->x != p->y, "token_mix fwd: x and y must not alias");
 
     CUtensorMap tmU, tmDY, tmX, tmS;

@@ -109,8 +109,6 @@ def test_token_mix_fwd_spill(B, P, D):
     # tanh.approx QuickGELU + bf16 rounding: 2^-8 of the element scale
     assert (got - ref["Hb"]).abs().max().item() <= 2 ** -7 * ref["Hb"].abs().max().item()
     assert _rel(got, ref["Hb"]) <= 6e-3
-    if sld > H:
-        assert (spill[:, :, H:] == 3.0).all()            # TMA clips the store at 4P columns
     assert _rel(y.double() - t["x"].double(), ref["Y"] - t["x"].double()) <= 4e-3
 
 

@@ -61,10 +61,13 @@ def main():
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--only", default="")
+    ap.add_argument("--tower", default="")
     a = ap.parse_args()
     which = [w for w in a.only.split(",") if w]
     res = {}
     for tag, P, D in (("image_P50_D768", 50, 768), ("text_P77_D512", 77, 512)):
+        if a.tower and not tag.startswith(a.tower):
+            continue
         res[tag] = run(a.batch, P, D, a.iters, a.nbuf, which)
     print(json.dumps(res))
     for tag, r in res.items():
