@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmixerclip.so")
+# MC_LIB selects another build of the same library (e.g. the -DTM_TRACE debug build of tools/tokenmix_trace.sh)
+LIB_PATH = os.environ.get("MC_LIB") or os.path.join(_HERE, "libmixerclip.so")
 
 F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
@@ -47,7 +48,6 @@ class TokenMixParams(C.Structure):
         ("w1", C.c_void_p), ("ld1", C.c_int64), ("b1", C.c_void_p),
         ("w2", C.c_void_p), ("ld2", C.c_int64), ("b2", C.c_void_p),
         ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p),
-        ("spill", C.c_void_p), ("spill_ld", C.c_int64),
         ("gw1", C.c_void_p), ("ldg1", C.c_int64), ("gw2", C.c_void_p), ("ldg2", C.c_int64), ("gb1", C.c_void_p),
     ]
 

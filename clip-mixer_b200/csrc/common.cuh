@@ -136,6 +136,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Wait for warps that are not on the critical path of a pipeline (epilogue warps polling for an accumulator): backs
+// off with nanosleep so that the polling does not take issue slots from the warp that feeds the tensor pipe (the
+// scheduler favours high warp ids, the MMA issuer is a single thread).  Watchdog by iteration count.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(sleep_ns);
+        if (++spins > (1u << 24)) {
+            printf("[mixerclip] mbarrier timeout (relaxed): block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x,
+                   blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PTX: TMA
 // ---------------------------------------------------------------------------------------------

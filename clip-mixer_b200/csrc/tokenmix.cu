@@ -20,14 +20,18 @@
 // tile each (w1t[p][j] = W1[j][p], w2t[p][j] = W2[p][j]); the same bytes serve as the MN-major B operand of the
 // "up" GEMMs (N = j, K = p) and as the K-major B operand of the "down" GEMMs (N = p, K = j).
 //
-//   warp 0      TMA producer: activation tiles (bf16 [P x 128] as two 64-wide swizzled groups) + L2 prefetch of the
+//   warps 0-7   E2: TMEM -> + residual + bias -> global (forward) / plain store (dgrad)
+//   warps 8-15  E1: TMEM -> bias + QuickGELU (or QuickGELU' product) -> bf16 -> smem operand tile
+//   warp 16     TMA producer: activation tiles (bf16 [P x 128] as two 64-wide swizzled groups) + L2 prefetch of the
 //               fp32 residual tile
-//   warp 1      MMA issuer (one thread)
-//   warp 2      TMEM allocator
-//   warp 3      optional TMA store of the bf16 H^T / dZ1^T tile ("spill", layout [B, D, 4P]) for an unfused consumer
-//   warps 4-11  E1: TMEM -> bias + QuickGELU (or QuickGELU' product) -> bf16 -> smem operand tile
-//   warps 12-19 E2: TMEM -> + residual + bias -> global (forward) / plain store (dgrad)
-//   WGRAD mode: warps 12-19 idle; the weight-gradient accumulators stay in TMEM across all tiles of the CTA.
+//   warp 17     TMEM allocator
+//   warp 19     MMA issuer (one thread)
+//   WGRAD mode: warps 0-7 idle; the weight-gradient accumulators stay in TMEM across all tiles of the CTA.
+// Role order matters: the warp scheduler favours the highest warp id of an SM sub-partition, the MMAs here are tiny
+// (32-64 clocks each), so the kernel is paced by how fast ONE thread gets its tcgen05.mma / commit / try_wait
+// instructions issued (measured with the -DTM_TRACE timeline: with the MMA issuer as warp 1 below sixteen polling
+// epilogue warps it needed ~1000 clocks per four MMAs).  Waiting epilogue warps back off with nanosleep.
+#include <cuda_fp16.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -39,21 +43,33 @@ namespace {
 constexpr int kE1Warps = 8;
 constexpr int kE2Warps = 8;
 constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 640
+constexpr int kProdWarp = 16, kAllocWarp = 17, kMmaWarp = 19;
 constexpr int kMaxAtoms = 5;                                   // hidden width 4P <= 320
 constexpr int kMaxTmStages = 2;
 constexpr uint32_t kAtomBytes = 128 * 128;                     // [128 rows x 64 bf16] swizzled K-major atom
 
 enum { TM_FWD = 0, TM_DGRAD = 1, TM_WGRAD = 2 };
 
+// Debug timeline (build with -DTM_TRACE, see tools/tokenmix_trace.sh): CTA 0 records (tag, clock) per role.
+#ifdef TM_TRACE
+__device__ unsigned long long g_tm_trace[20][1024];
+#define TM_TR(role, tag)                                                                                   \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && lane == 0 && tr_ctr < 1024)                                                 \
+            g_tm_trace[role][tr_ctr++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); \
+    } while (0)
+#else
+#define TM_TR(role, tag) do { } while (0)
+#endif
+
 struct TmArgs {
     int B, P, D, H;
     int Ppad, Hpad, natoms;
     int tiles_d, num_tiles;
-    int nseg, seg_c0[4], seg_w[4];
-    int zcols;                // TMEM columns of one working buffer (multiple of 32)
+    int SW;                   // hidden columns per pipeline segment (multiple of 64): 128 forward, 64 backward
     int stages;
     uint32_t grp_bytes;       // Ppad * 128: one [Ppad x 64] swizzled group of an activation / weight tile
-    uint32_t a_grp_bytes;     // group pitch of the activation tiles in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
+    uint32_t a_grp_bytes;     // group pitch of the U tile in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
     uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2;
     const __nv_bfloat16* w1;
     int ld1;
@@ -63,9 +79,7 @@ struct TmArgs {
     const float* b2;
     const float* x;
     float* y;
-    int spill;
-    // WGRAD
-    int j0, jw;               // hidden slice [j0, j0 + jw) of this launch's CTAs comes from blockIdx (see kernel)
+    // WGRAD: the hidden units are dealt to CTAs in slices of slice_w columns
     int nslices, slice_w;
     float* gw1;               // [4P, ldg1] fp32, +=
     int ldg1;
@@ -83,40 +97,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ bool tm_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tm_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tm_tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
 }
 __device__ __forceinline__ void tm_tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
-__device__ __forceinline__ void tm_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tm_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tm_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// tanh.approx.f32 runs at the full MUFU rate (16 lanes/clk/SM, measured with tools/ubench/mufu_rate.cu; the packed
+// f16x2 form is split into two MUFU ops and gains nothing).  sigmoid(1.702 z) = 0.5 + 0.5 tanh(0.851 z) costs one
+// MUFU op per element where ex2 + rcp costs two.
+__device__ __forceinline__ float2 tm_tanh2(float2 a) { return make_float2(tanh_approx(a.x), tanh_approx(a.y)); }
 // QuickGELU (model.py:175-177) on packed pairs: x * sigmoid(1.702 x) = hx + hx * tanh(0.851 x)
 __device__ __forceinline__ float2 tm_gelu2(float2 x) {
-    const float2 a = __fmul2_rn(x, make_float2(0.851f, 0.851f));
-    const float2 t = make_float2(tanh_approx(a.x), tanh_approx(a.y));
+    const float2 t = tm_tanh2(__fmul2_rn(x, make_float2(0.851f, 0.851f)));
     const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
     return __ffma2_rn(hx, t, hx);
 }
-// sigmoid from ex2 + rcp (~1 ulp each): the derivative multiplies every gradient that flows through the block
+// sigmoid(1.702 z) = 0.5 + 0.5 tanh(0.851 z)
 __device__ __forceinline__ float2 tm_sigmoid2(float2 z) {
-    const float2 a = __fmul2_rn(z, make_float2(-2.4554669595930157f, -2.4554669595930157f));   // -1.702 * log2(e) * z
-    float ex, ey, sx, sy;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(a.y));
-    const float2 den = __fadd2_rn(make_float2(ex, ey), make_float2(1.0f, 1.0f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sx) : "f"(den.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sy) : "f"(den.y));
-    return make_float2(sx, sy);
+    const float2 t = tm_tanh2(__fmul2_rn(z, make_float2(0.851f, 0.851f)));
+    return __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
 }
 __device__ __forceinline__ float2 tm_gelu_grad_from_s(float2 z, float2 s) {
     const float2 w = __fmul2_rn(z, make_float2(kGeluA, kGeluA));
@@ -125,97 +133,120 @@ __device__ __forceinline__ float2 tm_gelu_grad_from_s(float2 z, float2 s) {
     return __ffma2_rn(t1, s, s);                 // s + w s (1 - s)
 }
 
-// Weights -> resident swizzled tiles.  Element (p, j) of a tile lives at
-//   (j / 64) * grp_bytes + p * 128 + (((j % 64) / 8) ^ (p % 8)) * 16 + (j % 8) * 2
+// Weights -> resident swizzled tiles.  Element (p, jl) of a tile lives at
+//   (jl / 64) * grp_bytes + p * 128 + (((jl % 64) / 8) ^ (p % 8)) * 16 + (jl % 8) * 2
 // which is exactly what TMA's SWIZZLE_128B would produce for a [Ppad x 64] box of a [P x 4P] row-major matrix.
-// Only the hidden slice [jbase, jbase + natoms * 64) is loaded (tile-local column jl = j - jbase).
+// Only the hidden slice [jbase, jbase + natoms * 64) is loaded (tile-local column jl = j - jbase).  Called by all
+// threads; contains block-wide barriers.
 __device__ __forceinline__ void load_weight_tiles(const TmArgs& g, uint32_t w1t, uint32_t w2t, int jbase, int natoms) {
     const int chunks_per_row = natoms * 8;
     const int total = g.Ppad * chunks_per_row;
+    // w2t[p][jl] = W2[p][jbase + jl]: 16-byte vector loads along j (row pitch and jbase are multiples of 8); w1t zeroed
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-        const int grp = cj >> 3, c = cj & 7, jl = cj * 8, j = jbase + jl;
-        uint32_t v1[4] = {0u, 0u, 0u, 0u}, v2[4] = {0u, 0u, 0u, 0u};
-        if (p < g.P) {
-            unsigned short t1[8], t2[8];
+        const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (p < g.P && j < g.H) {
+            const uint4 t = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            if (j + 8 > g.H) {   // pad elements of the last chunk are not trusted
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool ok = j + e < g.H;
-                t1[e] = ok ? reinterpret_cast<const unsigned short*>(g.w1)[(long long)(j + e) * g.ld1 + p] : (unsigned short)0;
-                t2[e] = ok ? reinterpret_cast<const unsigned short*>(g.w2)[(long long)p * g.ld2 + j + e] : (unsigned short)0;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                v1[e] = (uint32_t)t1[2 * e] | ((uint32_t)t1[2 * e + 1] << 16);
-                v2[e] = (uint32_t)t2[2 * e] | ((uint32_t)t2[2 * e + 1] << 16);
+                for (int e = 0; e < 8; ++e)
+                    if (j + e >= g.H) v[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
             }
         }
         const uint32_t off = (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
-        tm_sts128(w1t + off, v1[0], v1[1], v1[2], v1[3]);
-        tm_sts128(w2t + off, v2[0], v2[1], v2[2], v2[3]);
+        tm_sts128(w2t + off, v[0], v[1], v[2], v[3]);
+        tm_sts128(w1t + off, 0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    // w1t[p][jl] = W1[jbase + jl][p]: 16-byte vector loads along p, scattered as 2-byte stores (a transpose)
+    const int pchunks = g.Ppad / 8, jn = natoms * 64;
+    for (int idx = threadIdx.x; idx < jn * pchunks; idx += blockDim.x) {
+        const int jl = idx / pchunks, pc = idx - jl * pchunks;
+        const int j = jbase + jl, p0 = pc * 8;
+        if (j < g.H && p0 < g.P) {
+            const uint4 t = *reinterpret_cast<const uint4*>(g.w1 + (long long)j * g.ld1 + p0);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+            const uint32_t cbase = (uint32_t)(jl >> 6) * g.grp_bytes + (uint32_t)(jl & 7) * 2u;
+            const uint32_t c = (uint32_t)((jl & 63) >> 3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int p = p0 + e;
+                if (p < g.P) {
+                    const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(w1t + cbase + (uint32_t)p * 128u + ((c ^ (uint32_t)(p & 7)) << 4)), "h"(h) : "memory");
+                }
+            }
+        }
     }
 }
 
-template <int MODE>
+// MODE: TM_FWD / TM_DGRAD / TM_WGRAD.  TD: compile-time channel count D (0 = run time) - with it every global access of
+// the E2 warps is a single LDG / STG with an immediate offset.
+template <int MODE, int TD>
 __global__ void __launch_bounds__(kTmThreads, 1)
 token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmDY,
-                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmS, const TmArgs g) {
+                 const __grid_constant__ CUtensorMap tmX, const TmArgs g) {
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t u_full[kMaxTmStages];
     __shared__ __align__(8) uint64_t u_empty[kMaxTmStages];
-    __shared__ __align__(8) uint64_t z_full, z_empty, h_empty;
+    __shared__ __align__(8) uint64_t z_full[2];
+    __shared__ __align__(8) uint64_t z_empty[2];
     __shared__ __align__(8) uint64_t h_full[kMaxAtoms];
+    __shared__ __align__(8) uint64_t h_empty[kMaxAtoms];
     __shared__ __align__(8) uint64_t y_full[2];
     __shared__ __align__(8) uint64_t y_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    [[maybe_unused]] int tr_ctr = 0;
     const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
-    const uint32_t w1t = base + g.off_w1t, w2t = base + g.off_w2t, hbuf = base + g.off_h;
+    const uint32_t w1t = base + g.off_w1t, w2t = base + g.off_w2t, hbuf = base + g.off_h, h2buf = base + g.off_h2;
     float* b1s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b1);
     float* b2s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b2);
-    constexpr int kYBufs = MODE == TM_FWD ? 2 : 1;
+    const int SW = g.SW;      // hidden columns per pipeline segment (multiple of 64)
     // WGRAD: CTAs are dealt round-robin to the hidden slices; every slice walks over all tiles
     const int slice = MODE == TM_WGRAD ? (int)(blockIdx.x % g.nslices) : 0;
     const int jbase = MODE == TM_WGRAD ? slice * g.slice_w : 0;
     const int work0 = MODE == TM_WGRAD ? (int)(blockIdx.x / g.nslices) : (int)blockIdx.x;
     const int work_stride = MODE == TM_WGRAD ? (int)(gridDim.x / g.nslices) : (int)gridDim.x;
-    const bool active = MODE != TM_WGRAD || (int)blockIdx.x < work_stride * g.nslices;
     // hidden columns handled by this CTA (tile-local: column c <-> hidden unit jbase + c)
-    int my_hpad = g.Hpad, my_atoms = g.natoms;
-    if (MODE == TM_WGRAD) {
-        my_hpad = g.Hpad - jbase < g.slice_w ? g.Hpad - jbase : g.slice_w;
-        my_atoms = (my_hpad + 63) / 64;
-    }
+    int my_hpad = g.Hpad;
+    if (MODE == TM_WGRAD) my_hpad = g.Hpad - jbase < g.slice_w ? g.Hpad - jbase : g.slice_w;
+    const int my_atoms = (my_hpad + 63) / 64;
+    const int nseg = (my_hpad + SW - 1) / SW;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kProdWarp && lane == 0) {
         tma_prefetch_desc(&tmU);
         if (MODE != TM_FWD) tma_prefetch_desc(&tmDY);
         if (MODE == TM_FWD) tma_prefetch_desc(&tmX);
-        if (g.spill) tma_prefetch_desc(&tmS);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 18 && lane == 0) {
         for (int s = 0; s < kMaxTmStages; ++s) {
             mbar_init(smem_u32(&u_full[s]), 1);
             mbar_init(smem_u32(&u_empty[s]), 1);
         }
-        mbar_init(smem_u32(&z_full), 1);
-        mbar_init(smem_u32(&z_empty), kE1Warps);
-        mbar_init(smem_u32(&h_empty), g.spill ? 2 : 1);
-        for (int a = 0; a < kMaxAtoms; ++a) mbar_init(smem_u32(&h_full[a]), kE1Warps);
         for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&z_full[s]), 1);
+            mbar_init(smem_u32(&z_empty[s]), kE1Warps);
             mbar_init(smem_u32(&y_full[s]), 1);
             mbar_init(smem_u32(&y_empty[s]), kE2Warps);
         }
+        for (int a = 0; a < kMaxAtoms; ++a) {
+            // an atom whose second 32-column chunk lies beyond the hidden width is written by 4 of the 8 E1 warps
+            mbar_init(smem_u32(&h_full[a]), (my_hpad - a * 64 > 32) ? kE1Warps : kE1Warps / 2);
+            mbar_init(smem_u32(&h_empty[a]), 1);
+        }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tmem_alloc(smem_u32(&tmem_base_smem), 512);
         tmem_relinquish();
     }
     // resident operands
-    load_weight_tiles(g, w1t, w2t, jbase, MODE == TM_WGRAD ? my_atoms : g.natoms);
+    load_weight_tiles(g, w1t, w2t, jbase, my_atoms);
     for (int i = threadIdx.x; i < g.natoms * 64; i += blockDim.x) b1s[i] = (jbase + i < g.H) ? g.b1[jbase + i] : 0.f;
     if (MODE == TM_FWD)
         for (int i = threadIdx.x; i < g.Ppad; i += blockDim.x) b2s[i] = i < g.P ? g.b2[i] : 0.f;
@@ -237,20 +268,20 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    // TMEM column map
-    const uint32_t col_z = 0, col_dh = g.zcols;
-    const uint32_t col_y = MODE == TM_FWD ? (uint32_t)g.zcols : 2u * g.zcols;          // FWD: Y0, Y1; DGRAD: dU
-    const uint32_t col_acc2 = 2u * g.zcols, col_acc1 = 2u * g.zcols + g.slice_w;       // WGRAD: dW2 / dW1^T accumulators
+    if (warp == 18) TM_TR(18, 1);
+    // TMEM column map: two rotating working buffers (FWD: Z; else Z and dH side by side), then the output tile(s)
+    const uint32_t wbuf_cols = MODE == TM_FWD ? (uint32_t)SW : 2u * SW;
+    const uint32_t col_y = 2u * wbuf_cols;                                              // FWD: Y0, Y1; DGRAD: dU0, dU1
+    const uint32_t col_acc2 = 2u * wbuf_cols, col_acc1 = 2u * wbuf_cols + g.slice_w;    // WGRAD: dW2 / dW1^T accumulators
 
-    if (!active) {
-        // nothing to do for this CTA (WGRAD with a grid that is not a multiple of the slice count)
-    } else if (warp == 0) {
+    if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
             for (int t = work0; t < g.num_tiles; t += work_stride) {
                 const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
-                mbar_wait(smem_u32(&u_empty[st]), ph ^ 1u);
+                mbar_wait_relaxed(smem_u32(&u_empty[st]), ph ^ 1u, 32);
+                TM_TR(kProdWarp, 1);
                 const uint32_t bar = smem_u32(&u_full[st]);
                 const uint32_t dst = base + g.off_stage + st * g.stage_bytes;
                 mbar_arrive_expect_tx(bar, (MODE == TM_FWD ? 2u : 4u) * g.grp_bytes);
@@ -271,142 +302,165 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t st = 0, ph = 0, zph = 0, hph = 0, yb = 0, yph[2] = {0u, 0u};
+        // Software pipeline over hidden segments: the "up" GEMMs of tile i, segment s are issued right before the
+        // "down" GEMMs of tile i-1, segment s, so the tensor pipe works on tile i while the E1 warps still convert
+        // tile i-1 (the working TMEM buffers rotate per segment, the bf16 operand atoms are released per atom).
+        // The whole warp runs this loop (every value in it is warp-uniform, so descriptors and addresses can live in
+        // uniform registers); one elected lane issues the tcgen05 instructions, in groups of up to 5 per branch.  With a
+        // single-lane `if (lane == 0)` body the compiler spent ~30 instructions (R2UR moves, an ELECT retry loop) per
+        // 32-clock MMA and this one thread paced the whole kernel (-DTM_TRACE timeline).
+        {
+            const bool leader = tm_elect_one();
+            uint32_t st = 0, ph = 0, sc = 0, n = 0;
+            bool have_prev = false;
+            uint32_t pn = 0, pst = 0;
             const uint32_t idesc_dn = make_idesc_bf16(128, g.Ppad, 0, 0);
-            bool first_tile = true;
+            const uint32_t wdn = MODE == TM_FWD ? w2t : w1t;
+            const int ksteps_up = g.Ppad / 16;    // 1 .. 5
+            // descriptor templates: the start-address field (bits 0-13, address >> 4) is added per instruction
+            const uint64_t dK = make_sdesc_sw128(0u, 16u, 1024u);                 // K-major operand
+            const uint64_t dMNg = make_sdesc_sw128(0u, g.grp_bytes, 1024u);       // MN-major, 64-wide groups grp_bytes apart
+            const uint64_t dMNa = make_sdesc_sw128(0u, g.a_grp_bytes, 1024u);     // MN-major U tile
+            const uint64_t dMNh = make_sdesc_sw128(0u, kAtomBytes, 1024u);        // MN-major view of the H^T / dZ1^T atoms
+            auto down_seg = [&](int s) {
+                const int a0 = (s * SW) >> 6;
+                int a1 = ((s + 1) * SW) >> 6;
+                if (a1 > my_atoms) a1 = my_atoms;
+                if (MODE == TM_WGRAD) {
+                    // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels)
+                    const uint32_t u_base = base + g.off_stage + pst * g.stage_bytes;
+                    const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
+                    for (int a = a0; a < a1; ++a) {
+                        mbar_wait(smem_u32(&h_full[a]), pn & 1u);
+                        tc_fence_after();
+                        const int wn = my_hpad - a * 64 < 64 ? my_hpad - a * 64 : 64;
+                        const uint32_t idesc_w = make_idesc_bf16(128, wn, 0, 1);
+                        // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B (+2)
+                        // B (MN-major): K = channel rows of the [128 d x 64 j] atom, 16 rows = 2048 B (+128)
+                        const uint64_t b_h = dMNh + ((hbuf + a * kAtomBytes) >> 4), b_dz = dMNh + ((h2buf + a * kAtomBytes) >> 4);
+                        const uint32_t acc2 = tmem_base + col_acc2 + a * 64, acc1 = tmem_base + col_acc1 + a * 64;
+                        const uint32_t accum0 = pn > 0 ? 1u : 0u;
+                        if (leader) {
+#pragma unroll
+                            for (int hlf = 0; hlf < 2; ++hlf) {
+                                const uint64_t a_dy = dK + ((dy_base + hlf * g.grp_bytes) >> 4);
+                                const uint64_t a_u = dK + ((u_base + hlf * g.a_grp_bytes) >> 4);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    const int ks = hlf * 4 + k4;
+                                    umma_ss(acc2, a_dy + 2 * k4, b_h + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
+                                    umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
+                                }
+                            }
+                            umma_commit(smem_u32(&h_empty[a]));
+                        }
+                    }
+                    if (s == nseg - 1 && leader) umma_commit(smem_u32(&u_empty[pst]));
+                } else {
+                    const uint32_t yb = pn & 1u;
+                    if (s == 0) {
+                        mbar_wait(smem_u32(&y_empty[yb]), ((pn >> 1) & 1u) ^ 1u);
+                        TM_TR(kMmaWarp, 4);
+                        tc_fence_after();
+                    }
+                    const uint32_t d_tmem = tmem_base + col_y + yb * g.Ppad;
+                    for (int a = a0; a < a1; ++a) {
+                        mbar_wait(smem_u32(&h_full[a]), pn & 1u);
+                        TM_TR(kMmaWarp, 5);
+                        tc_fence_after();
+                        const int ksteps = (my_hpad - a * 64) >= 64 ? 4 : (my_hpad - a * 64) / 16;
+                        const uint64_t ad = dK + ((hbuf + a * kAtomBytes) >> 4), bd = dK + ((wdn + a * g.grp_bytes) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (kk < ksteps) umma_ss(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc_dn, (a > 0 || kk > 0) ? 1u : 0u);
+                            umma_commit(smem_u32(&h_empty[a]));
+                            if (a == my_atoms - 1) umma_commit(smem_u32(&y_full[yb]));
+                        }
+                    }
+                }
+            };
             for (int t = work0; t < g.num_tiles; t += work_stride) {
+                TM_TR(kMmaWarp, 1);
                 mbar_wait(smem_u32(&u_full[st]), ph);
+                TM_TR(kMmaWarp, 2);
                 tc_fence_after();
                 const uint32_t u_base = base + g.off_stage + st * g.stage_bytes;
                 const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
-                // ---- "up" GEMMs: Z^T = U^T W1^T (and dH^T = dY^T W2), one hidden segment at a time ----
-                for (int s = 0; s < g.nseg; ++s) {
-                    mbar_wait(smem_u32(&z_empty), zph ^ 1u);
-                    zph ^= 1u;
+                const uint64_t ad_u = dMNa + (u_base >> 4), ad_dy = dMNg + (dy_base >> 4);
+                for (int s = 0; s < nseg; ++s) {
+                    // ---- "up" GEMMs of this tile: Z^T = U^T W1^T (and dH^T = dY^T W2) for hidden segment s ----
+                    const uint32_t b = sc & 1u;
+                    mbar_wait(smem_u32(&z_empty[b]), ((sc >> 1) & 1u) ^ 1u);
+                    TM_TR(kMmaWarp, 3);
                     tc_fence_after();
-                    int c = 0;
-                    const int sw = MODE == TM_WGRAD ? my_hpad : g.seg_w[s];
-                    while (c < sw) {
-                        int w = sw - c;
-                        if (w > 256) w = 192;
-                        const uint32_t idesc_up = make_idesc_bf16(128, w, 1, 1);
-                        const uint32_t grp0 = (uint32_t)((g.seg_c0[s] + c) >> 6);
-                        for (int ks = 0; ks < g.Ppad / 16; ++ks) {
-                            const uint64_t ad = make_sdesc_sw128(u_base + ks * 2048, g.a_grp_bytes, 1024u);
-                            const uint64_t bd = make_sdesc_sw128(w1t + grp0 * g.grp_bytes + ks * 2048, g.grp_bytes, 1024u);
-                            umma_ss(tmem_base + col_z + c, ad, bd, idesc_up, ks > 0 ? 1u : 0u);
-                            if (MODE != TM_FWD) {
-                                const uint64_t ad2 = make_sdesc_sw128(dy_base + ks * 2048, g.grp_bytes, 1024u);
-                                const uint64_t bd2 = make_sdesc_sw128(w2t + grp0 * g.grp_bytes + ks * 2048, g.grp_bytes, 1024u);
-                                umma_ss(tmem_base + col_dh + c, ad2, bd2, idesc_up, ks > 0 ? 1u : 0u);
+                    const int c0 = s * SW;
+                    const int w = my_hpad - c0 < SW ? my_hpad - c0 : SW;
+                    const uint32_t idesc_up = make_idesc_bf16(128, w, 1, 1);
+                    const uint32_t goff = (uint32_t)(c0 >> 6) * g.grp_bytes;
+                    const uint64_t bd_1 = dMNg + ((w1t + goff) >> 4), bd_2 = dMNg + ((w2t + goff) >> 4);
+                    const uint32_t zcol = tmem_base + b * wbuf_cols;
+                    if (leader) {
+                        // k-step = 16 token rows of the [Ppad x 64] groups = 2048 B (+128 in the descriptor)
+#pragma unroll
+                        for (int ks = 0; ks < 5; ++ks) {
+                            if (ks < ksteps_up) {
+                                umma_ss(zcol, ad_u + 128 * ks, bd_1 + 128 * ks, idesc_up, ks > 0 ? 1u : 0u);
+                                if (MODE != TM_FWD) umma_ss(zcol + SW, ad_dy + 128 * ks, bd_2 + 128 * ks, idesc_up, ks > 0 ? 1u : 0u);
                             }
                         }
-                        c += w;
+                        if (MODE != TM_WGRAD && s == nseg - 1) umma_commit(smem_u32(&u_empty[st]));
+                        umma_commit(smem_u32(&z_full[b]));
                     }
-                    if (MODE != TM_WGRAD && s == g.nseg - 1) umma_commit(smem_u32(&u_empty[st]));
-                    umma_commit(smem_u32(&z_full));
+                    ++sc;
+                    // ---- "down" GEMMs of the previous tile, same segment ----
+                    if (have_prev) down_seg(s);
                 }
-                // ---- "down" GEMMs ----
-                if (MODE == TM_WGRAD) {
-                    // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels)
-                    const uint32_t idesc_w = make_idesc_bf16(128, my_hpad, 0, 1);
-                    const uint32_t h2buf = base + g.off_h2;
-                    for (int a = 0; a < my_atoms; ++a) {
-                        mbar_wait(smem_u32(&h_full[a]), hph);
-                    }
-                    tc_fence_after();
-                    for (int ks = 0; ks < 8; ++ks) {
-                        // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B
-                        const uint32_t aoff = (uint32_t)(ks >> 2) * g.a_grp_bytes + (uint32_t)(ks & 3) * 32u;
-                        const uint64_t a_dy = make_sdesc_sw128(dy_base + (uint32_t)(ks >> 2) * g.grp_bytes + (uint32_t)(ks & 3) * 32u, 16u, 1024u);
-                        const uint64_t a_u = make_sdesc_sw128(u_base + aoff, 16u, 1024u);
-                        // B (MN-major): K = channel rows of the [128 d x 64 j] atoms, 16 rows = 2048 B; groups of 64 j = atoms
-                        const uint64_t b_h = make_sdesc_sw128(hbuf + ks * 2048, kAtomBytes, 1024u);
-                        const uint64_t b_dz = make_sdesc_sw128(h2buf + ks * 2048, kAtomBytes, 1024u);
-                        umma_ss(tmem_base + col_acc2, a_dy, b_h, idesc_w, (!first_tile || ks > 0) ? 1u : 0u);
-                        umma_ss(tmem_base + col_acc1, a_u, b_dz, idesc_w, (!first_tile || ks > 0) ? 1u : 0u);
-                    }
-                    hph ^= 1u;
-                    umma_commit(smem_u32(&u_empty[st]));
-                    umma_commit(smem_u32(&h_empty));
-                } else {
-                    mbar_wait(smem_u32(&y_empty[yb]), yph[yb] ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + col_y + yb * g.Ppad;
-                    const uint32_t wdn = MODE == TM_FWD ? w2t : w1t;
-                    for (int a = 0; a < g.natoms; ++a) {
-                        mbar_wait(smem_u32(&h_full[a]), hph);
-                        tc_fence_after();
-                        const int ksteps = (g.Hpad - a * 64) >= 64 ? 4 : (g.Hpad - a * 64) / 16;
-                        for (int kk = 0; kk < ksteps; ++kk) {
-                            const uint64_t ad = make_sdesc_sw128(hbuf + a * kAtomBytes + kk * 32, 16u, 1024u);
-                            const uint64_t bd = make_sdesc_sw128(wdn + a * g.grp_bytes + kk * 32, 16u, 1024u);
-                            umma_ss(d_tmem, ad, bd, idesc_dn, (a > 0 || kk > 0) ? 1u : 0u);
-                        }
-                    }
-                    hph ^= 1u;
-                    umma_commit(smem_u32(&h_empty));
-                    umma_commit(smem_u32(&y_full[yb]));
-                    yph[yb] ^= 1u;
-                    yb = (yb + 1) % kYBufs;
-                }
-                first_tile = false;
+                have_prev = true;
+                pn = n;
+                pst = st;
+                ++n;
                 if (++st == (uint32_t)g.stages) {
                     st = 0;
                     ph ^= 1u;
                 }
             }
-            if (MODE == TM_WGRAD) umma_commit(smem_u32(&y_full[0]));   // accumulators final
+            if (have_prev)
+                for (int s = 0; s < nseg; ++s) down_seg(s);
+            if (MODE == TM_WGRAD && leader) umma_commit(smem_u32(&y_full[0]));   // accumulators final
         }
-    } else if (warp == 3) {
-        // ===================== spill: TMA store of the bf16 operand tile =====================
-        if (g.spill && lane == 0 && MODE != TM_WGRAD) {
-            uint32_t hph = 0;
-            for (int t = work0; t < g.num_tiles; t += work_stride) {
-                const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
-                for (int a = 0; a < g.natoms; ++a) {
-                    mbar_wait(smem_u32(&h_full[a]), hph);
-                    tm_tma_store_3d(&tmS, hbuf + a * kAtomBytes, a * 64, d0, b);
-                }
-                tm_bulk_commit();
-                tm_bulk_wait_read0();
-                mbar_arrive(smem_u32(&h_empty));
-                hph ^= 1u;
-            }
-            tm_bulk_wait_all();
-        }
-    } else if (warp >= 4 && warp < 4 + kE1Warps) {
+    } else if (warp >= kE2Warps && warp < kE2Warps + kE1Warps) {
         // ===================== E1: hidden activation TMEM -> bf16 smem operand =====================
-        const int e = warp - 4;
+        const int e = warp - kE2Warps;
         const int q = e & 3, par = e >> 2;
         const int r = q * 32 + lane;                         // tile row = channel d0 + r
         const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        uint32_t zfph = 0, heph = 0;
-        for (int t = work0; t < g.num_tiles; t += work_stride) {
-            for (int s = 0; s < g.nseg; ++s) {
-                mbar_wait(smem_u32(&z_full), zfph);
-                zfph ^= 1u;
+        uint32_t sc = 0, n = 0;
+        for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
+            for (int s = 0; s < nseg; ++s, ++sc) {
+                const uint32_t b = sc & 1u;
+                TM_TR(warp, 1);
+                mbar_wait_relaxed(smem_u32(&z_full[b]), (sc >> 1) & 1u, 20);
+                TM_TR(warp, 2);
                 tc_fence_after();
-                if (s == 0) {
-                    mbar_wait(smem_u32(&h_empty), heph ^ 1u);
-                    heph ^= 1u;
-                }
-                const int c0 = g.seg_c0[s];
-                const int sw_cols = MODE == TM_WGRAD ? my_hpad : g.seg_w[s];
-                const int a_begin = c0 >> 6, a_end = (c0 + sw_cols + 63) >> 6;
-                for (int a = a_begin; a < a_end; ++a) {
+                const uint32_t zcol = t_lane + b * wbuf_cols;
+                const int a0 = (s * SW) >> 6;
+                int a1 = ((s + 1) * SW) >> 6;
+                if (a1 > my_atoms) a1 = my_atoms;
+                for (int a = a0; a < a1; ++a) {
                     const int col = a * 64 + par * 32;       // tile-local hidden column of this warp's chunk
-                    const int rel = col - c0;
-                    if (rel < sw_cols) {
+                    const int rel = col - s * SW;
+                    if (col < my_hpad) {
+                        mbar_wait_relaxed(smem_u32(&h_empty[a]), (n & 1u) ^ 1u, 20);   // the previous tile's down GEMMs released the atom
+                        TM_TR(warp, 3);
                         const uint32_t dst = hbuf + a * kAtomBytes + row_off;
                         if (MODE == TM_FWD) {
                             uint32_t v[32];
-                            tmem_ld32(t_lane + col_z + rel, v);
+                            tmem_ld32(zcol + rel, v);
                             tmem_ld_wait();
                             uint32_t o[16];
 #pragma unroll
@@ -420,12 +474,12 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                             for (int jj = 0; jj < 4; ++jj)
                                 tm_sts128(dst + (((uint32_t)(par * 4 + jj) ^ sw) << 4), o[4 * jj], o[4 * jj + 1], o[4 * jj + 2], o[4 * jj + 3]);
                         } else {
-                            const uint32_t dst2 = base + g.off_h2 + a * kAtomBytes + row_off;
+                            const uint32_t dst2 = h2buf + a * kAtomBytes + row_off;
 #pragma unroll
                             for (int hf = 0; hf < 2; ++hf) {
                                 uint32_t zv[16], dv[16];
-                                tmem_ld16(t_lane + col_z + rel + hf * 16, zv);
-                                tmem_ld16(t_lane + col_dh + rel + hf * 16, dv);
+                                tmem_ld16(zcol + rel + hf * 16, zv);
+                                tmem_ld16(zcol + SW + rel + hf * 16, dv);
                                 tmem_ld_wait();
                                 uint32_t o[8], oh[8];
 #pragma unroll
@@ -454,19 +508,20 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                                 }
                             }
                         }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&h_full[a]));
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&h_full[a]));
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&z_empty));
+                TM_TR(warp, 4);
+                if (lane == 0) mbar_arrive(smem_u32(&z_empty[b]));
             }
         }
         if (MODE == TM_WGRAD) {
             // ---- final: accumulators -> global gradients.  Lane = token p (or the ones-row Ppad -> db1) ----
-            mbar_wait(smem_u32(&y_full[0]), 0u);
+            mbar_wait_relaxed(smem_u32(&y_full[0]), 0u, 64);
             tc_fence_after();
             const int p = r;
             for (int c = par * 32; c < my_hpad; c += 64) {
@@ -488,61 +543,82 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= 4 + kE1Warps) {
+    } else if (warp < kE2Warps) {
         // ===================== E2: output accumulator -> global =====================
         if (MODE != TM_WGRAD) {
-            const int e2 = warp - 4 - kE1Warps;
+            const int e2 = warp;
             const int q = e2 & 3, hsel = e2 >> 2;
             const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
             const int nch = g.Ppad / 16;
-            uint32_t yb = 0, yph[2] = {0u, 0u};
-            for (int t = work0; t < g.num_tiles; t += work_stride) {
+            const int Dd = TD ? TD : g.D;
+            uint32_t n = 0;
+            for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
                 const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
-                const long long gbase = (long long)b * g.P * g.D + d0 + q * 32 + lane;
+                // this warp owns the 16-token chunks hsel, hsel + 2, hsel + 4: token p = hsel*16 + 32*k + i
+                const long long gbase = ((long long)b * g.P + hsel * 16) * Dd + d0 + q * 32 + lane;
+                const float* xt = g.x + gbase;
+                float* yt = g.y + gbase;
                 float xr[3][16];
                 if (MODE == TM_FWD) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const int ch = hsel + 2 * k;
+                        const int p0 = hsel * 16 + 32 * k;
+                        if (p0 + 16 <= g.P) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int p = ch * 16 + i;
-                            xr[k][i] = (ch < nch && p < g.P) ? __ldg(g.x + gbase + (long long)p * g.D) : 0.f;
+                            for (int i = 0; i < 16; ++i) xr[k][i] = __ldg(xt + (32 * k + i) * Dd);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) xr[k][i] = p0 + i < g.P ? __ldg(xt + (32 * k + i) * Dd) : 0.f;
                         }
                     }
                 }
-                mbar_wait(smem_u32(&y_full[yb]), yph[yb]);
-                yph[yb] ^= 1u;
+                const uint32_t yb = n & 1u;
+                TM_TR(warp, 1);
+                mbar_wait_relaxed(smem_u32(&y_full[yb]), (n >> 1) & 1u, 64);
+                TM_TR(warp, 2);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const int ch = hsel + 2 * k;
+                    const int ch = hsel + 2 * k, p0 = hsel * 16 + 32 * k;
                     if (ch < nch) {
                         uint32_t v[16];
                         tmem_ld16(t_lane + col_y + yb * g.Ppad + ch * 16, v);
-                        tmem_ld_wait();
+                        float o[16];
+                        if (MODE == TM_FWD) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int p = ch * 16 + i;
-                            if (p < g.P) {
-                                float o = __uint_as_float(v[i]);
-                                if (MODE == TM_FWD) o += b2s[p] + xr[k][i];
-                                g.y[gbase + (long long)p * g.D] = o;
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 bv = *reinterpret_cast<const float4*>(b2s + p0 + 4 * i4);
+                                o[4 * i4] = xr[k][4 * i4] + bv.x;
+                                o[4 * i4 + 1] = xr[k][4 * i4 + 1] + bv.y;
+                                o[4 * i4 + 2] = xr[k][4 * i4 + 2] + bv.z;
+                                o[4 * i4 + 3] = xr[k][4 * i4 + 3] + bv.w;
                             }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+                        }
+                        tmem_ld_wait();
+                        if (p0 + 16 <= g.P) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) yt[(32 * k + i) * Dd] = o[i] + __uint_as_float(v[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (p0 + i < g.P) yt[(32 * k + i) * Dd] = o[i] + __uint_as_float(v[i]);
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
+                TM_TR(warp, 3);
                 if (lane == 0) mbar_arrive(smem_u32(&y_empty[yb]));
-                yb = (yb + 1) % kYBufs;
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == kAllocWarp) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host ----------------------------------------------------------------------------------------------
@@ -578,17 +654,39 @@ int tm_make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int e
     return MC_OK;
 }
 
-template <int MODE>
-int tm_launch(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmS,
-              const TmArgs& g, int grid, size_t smem, cudaStream_t stream) {
+template <int MODE, int TD>
+int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const TmArgs& g, int grid, size_t smem,
+                cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
-    token_mix_kernel<MODE><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, tmS, g);
+    token_mix_kernel<MODE, TD><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, g);
     MC_CUDA(cudaGetLastError());
+#ifdef TM_TRACE
+    {
+        static unsigned long long host[20][1024];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(host, g_tm_trace, sizeof(host));
+        fprintf(stderr, "[tm_trace] mode %d P %d D %d\n", MODE, g.P, g.D);
+        for (int r = 0; r < 20; ++r)
+            for (int i = 0; i < 1024 && host[r][i] != 0; ++i)
+                fprintf(stderr, "[tm_trace] role %d ev %d tag %llu clk %llu\n", r, i, host[r][i] >> 48, host[r][i] & 0xffffffffffffull);
+        static unsigned long long zero[20][1024];
+        cudaMemcpyToSymbol(g_tm_trace, zero, sizeof(zero));
+    }
+#endif
     return MC_OK;
+}
+
+template <int MODE>
+int tm_launch(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const TmArgs& g, int grid, size_t smem,
+              cudaStream_t stream) {
+    // the two production widths get their own instantiation (immediate-offset global accesses in the E2 warps)
+    if (MODE != TM_WGRAD && g.D == 768) return tm_launch_t<MODE, 768>(tmU, tmDY, tmX, g, grid, smem, stream);
+    if (MODE != TM_WGRAD && g.D == 512) return tm_launch_t<MODE, 512>(tmU, tmDY, tmX, g, grid, smem, stream);
+    return tm_launch_t<MODE, 0>(tmU, tmDY, tmX, g, grid, smem, stream);
 }
 
 int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
@@ -612,40 +710,25 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     g.w1 = reinterpret_cast<const __nv_bfloat16*>(p->w1); g.ld1 = (int)p->ld1;
     g.w2 = reinterpret_cast<const __nv_bfloat16*>(p->w2); g.ld2 = (int)p->ld2;
     g.b1 = p->b1; g.b2 = p->b2; g.x = p->x; g.y = p->y;
-    g.spill = (p->spill != nullptr && mode != TM_WGRAD) ? 1 : 0;
-    MC_CHECK(g.ld1 >= g.P && g.ld2 >= g.H, "token_mix: weight pitches too small");
+    MC_CHECK(g.ld1 >= g.P && g.ld2 >= g.H && g.ld1 % 8 == 0 && g.ld2 % 8 == 0, "token_mix: weight pitches must be >= the row length and multiples of 8");
+    MC_CHECK((reinterpret_cast<uintptr_t>(p->w1) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w2) & 15) == 0,
+             "token_mix: weights must be 16-byte aligned");
 
     const int sms = sm_count();
     int grid = g.num_tiles < sms ? g.num_tiles : sms;
     int natoms_smem = g.natoms;
+    g.slice_w = 128;
+    g.nslices = 1;
+    // TMEM: two rotating working buffers (forward 2 x 128 columns of Z; backward 2 x (64 Z + 64 dH)) + 2 output tiles of
+    // Ppad columns, or (wgrad) two 128-column accumulators
+    g.SW = mode == TM_FWD ? 128 : 64;
     if (mode == TM_WGRAD) {
-        // accumulators 2 x slice_w + working buffers 2 x slice_w TMEM columns: slice_w = 128
-        g.slice_w = 128;
         g.nslices = (g.Hpad + g.slice_w - 1) / g.slice_w;
-        g.nseg = 1; g.seg_c0[0] = 0; g.seg_w[0] = g.slice_w;
-        g.zcols = g.slice_w;
         natoms_smem = g.slice_w / 64;
         MC_CHECK(p->gw1 && p->gw2 && p->gb1 && p->dy, "token_mix wgrad: null operand");
         g.gw1 = p->gw1; g.ldg1 = (int)p->ldg1; g.gw2 = p->gw2; g.ldg2 = (int)p->ldg2; g.gb1 = p->gb1;
         grid = sms / g.nslices * g.nslices;
         if (grid > g.num_tiles * g.nslices) grid = g.num_tiles * g.nslices;
-    } else {
-        // hidden segments: the working TMEM buffers (Z, and dH in dgrad) share 512 columns with the output tile(s)
-        const int cap = mode == TM_FWD ? 512 - 2 * g.Ppad : (512 - g.Ppad) / 2;
-        if (round_up_i(g.Hpad, 32) <= cap) {
-            g.nseg = 1; g.seg_c0[0] = 0; g.seg_w[0] = g.Hpad;
-        } else {
-            const int wseg = cap / 64 * 64;
-            g.nseg = 0;
-            for (int c = 0; c < g.Hpad; c += wseg) {
-                MC_CHECK(g.nseg < 4, "token_mix: too many hidden segments");
-                g.seg_c0[g.nseg] = c;
-                g.seg_w[g.nseg] = g.Hpad - c < wseg ? g.Hpad - c : wseg;
-                ++g.nseg;
-            }
-        }
-        g.zcols = 0;
-        for (int s = 0; s < g.nseg; ++s) g.zcols = g.zcols > round_up_i(g.seg_w[s], 32) ? g.zcols : round_up_i(g.seg_w[s], 32);
     }
     // shared memory plan (all offsets multiples of 1024)
     uint32_t off = 0;
@@ -669,15 +752,16 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     MC_CHECK(off + g.stage_bytes <= budget, "token_mix: shape does not fit in shared memory");
     g.stages = (int)((budget - off) / g.stage_bytes);
     if (g.stages > kMaxTmStages) g.stages = kMaxTmStages;
+    // wgrad keeps the activation tile of the previous work item alive while the next one is loaded
+    MC_CHECK(mode != TM_WGRAD || g.stages >= 2, "token_mix wgrad: shape does not fit in shared memory");
     size_t smem = (size_t)off + (size_t)g.stages * g.stage_bytes + 1024 + slack;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM (each allocates all of TMEM)
     MC_CHECK(smem <= 226 * 1024, "token_mix: shape does not fit in shared memory");
     MC_CHECK(mode != TM_FWD || p->x != p->y, "token_mix fwd: x and y must not alias");
 
-    CUtensorMap tmU, tmDY, tmX, tmS;
+    CUtensorMap tmU, tmDY, tmX;
     memset(&tmDY, 0, sizeof(tmDY));
     memset(&tmX, 0, sizeof(tmX));
-    memset(&tmS, 0, sizeof(tmS));
     int rc = tm_make_map(&tmU, p->u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.D, g.P, g.B, g.D, (int64_t)g.P * g.D, 64, g.Ppad,
                          CU_TENSOR_MAP_SWIZZLE_128B, "u");
     if (rc != MC_OK) return rc;
@@ -693,16 +777,10 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         if (rc != MC_OK) return rc;
     }
     if (mode == TM_DGRAD) MC_CHECK(p->y != nullptr, "token_mix dgrad: null output");
-    if (g.spill) {
-        MC_CHECK(p->spill_ld >= g.H, "token_mix: spill pitch too small");
-        rc = tm_make_map(&tmS, p->spill, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.H, g.D, g.B, p->spill_ld, (int64_t)g.D * p->spill_ld,
-                         64, 128, CU_TENSOR_MAP_SWIZZLE_128B, "spill");
-        if (rc != MC_OK) return rc;
-    }
     switch (mode) {
-        case TM_FWD: return tm_launch<TM_FWD>(tmU, tmDY, tmX, tmS, g, grid, smem, stream);
-        case TM_DGRAD: return tm_launch<TM_DGRAD>(tmU, tmDY, tmX, tmS, g, grid, smem, stream);
-        default: return tm_launch<TM_WGRAD>(tmU, tmDY, tmX, tmS, g, grid, smem, stream);
+        case TM_FWD: return tm_launch<TM_FWD>(tmU, tmDY, tmX, g, grid, smem, stream);
+        case TM_DGRAD: return tm_launch<TM_DGRAD>(tmU, tmDY, tmX, g, grid, smem, stream);
+        default: return tm_launch<TM_WGRAD>(tmU, tmDY, tmX, g, grid, smem, stream);
     }
 }
 

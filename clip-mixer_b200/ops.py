@@ -173,19 +173,19 @@ def _tm_call(fn, p, what, B, P, D):
     _count()
 
 
-def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2, spill=None, spill_ld=0):
+def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2):
     """y = x + W2 g(W1 u + b1) + b2 per sample (model.py:216,220-222), one fused kernel."""
     p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
-    p.b2, p.x, p.y, p.spill, p.spill_ld = _ptr(b2), _ptr(x), _ptr(y), _ptr(spill), spill_ld
+    p.b2, p.x, p.y = _ptr(b2), _ptr(x), _ptr(y)
     _tm_call(_lib.load().mc_token_mix_fwd, p, "token_mix_fwd", B, P, D)
 
 
-def token_mix_dgrad(B, P, D, u, dy, du, w1, ld1, b1, w2, ld2, spill=None, spill_ld=0):
+def token_mix_dgrad(B, P, D, u, dy, du, w1, ld1, b1, w2, ld2):
     """du = W1^T ((W2^T dy) * g'(W1 u + b1)) per sample, one fused kernel (dy bf16, du fp32)."""
     if dy.dtype != torch.bfloat16 or du.dtype != torch.float32:
         raise MixerClipError("token_mix_dgrad: dy must be bf16 and du fp32")
     p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
-    p.dy, p.y, p.spill, p.spill_ld = _ptr(dy), _ptr(du), _ptr(spill), spill_ld
+    p.dy, p.y = _ptr(dy), _ptr(du)
     _tm_call(_lib.load().mc_token_mix_dgrad, p, "token_mix_dgrad", B, P, D)
 
 

@@ -128,8 +128,6 @@ int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream);
  *   mc_token_mix_dgrad  y  = W1^T ( (W2^T dy) * g'(W1 u + b1) )                         (dy bf16 [B,P,D]; y = dU fp32)
  *   mc_token_mix_wgrad  gw2 += sum_b dy H1^T, gw1 += sum_b dZ1 u^T, gb1 += rowsum(dZ1)  (H1, dZ1 recomputed on chip)
  * w1 / w2 are the bf16 operand copies with row pitches ld1 / ld2 (multiples of 8, pad elements ignored).
- * spill (optional, fwd / dgrad): bf16 [B, D, spill_ld] copy of H1^T (fwd) or dZ1^T (dgrad) for an unfused consumer;
- * columns [4P, spill_ld) of it are unspecified.
  * Supported shapes: mc_token_mix_supported(P, D) != 0  (P <= 80 tokens, D a multiple of 128); other shapes
  * (B/16: 197 tokens) run the same math as separate mc_gemm_bf16_tc calls.
  * ------------------------------------------------------------------------------------------ */
@@ -145,8 +143,6 @@ typedef struct mc_token_mix_params {
     const float* x;
     float* y;
     const void* dy;
-    void* spill;
-    int64_t spill_ld;
     float* gw1;
     int64_t ldg1;
     float* gw2;

@@ -92,44 +92,18 @@ def test_token_mix_fwd(B, P, D):
     assert _rel(y.double() - t["x"].double(), ref["Y"] - t["x"].double()) <= 4e-3
 
 
-@pytest.mark.parametrize("B,P,D", SHAPES[:3])
-def test_token_mix_fwd_spill(B, P, D):
-    """The optional bf16 [B, D, 4P] copy of H1^T (layout for an unfused weight-gradient GEMM)."""
-    ops = _ops()
-    t = _setup(B, P, D, seed=3)
-    ref = _reference(t, P)
-    H = t["H"]
-    sld = (H + 7) // 8 * 8
-    y = torch.empty_like(t["x"])
-    spill = torch.full((B, D, sld), 3.0, device=y.device, dtype=torch.bfloat16)
-    ops.token_mix_fwd(B, P, D, t["u"], t["x"], y, t["w1"], t["ld1"], t["b1"], t["w2"], t["ld2"], t["b2"], spill=spill,
-                      spill_ld=sld)
-    torch.cuda.synchronize()
-    got = spill[:, :, :H].double().transpose(1, 2)      # [B, H, D]
-    # tanh.approx QuickGELU + bf16 rounding: 2^-8 of the element scale
-    assert (got - ref["Hb"]).abs().max().item() <= 2 ** -7 * ref["Hb"].abs().max().item()
-    assert _rel(got, ref["Hb"]) <= 6e-3
-    assert _rel(y.double() - t["x"].double(), ref["Y"] - t["x"].double()) <= 4e-3
-
-
 @pytest.mark.parametrize("B,P,D", SHAPES)
 def test_token_mix_dgrad(B, P, D):
     ops = _ops()
     t = _setup(B, P, D, seed=1)
     ref = _reference(t, P)
     du = torch.full_like(t["x"], float("nan"))
-    H = t["H"]
-    sld = (H + 7) // 8 * 8
-    spill = torch.zeros(B, D, sld, device=du.device, dtype=torch.bfloat16)
-    ops.token_mix_dgrad(B, P, D, t["u"], t["dy"], du, t["w1"], t["ld1"], t["b1"], t["w2"], t["ld2"], spill=spill,
-                        spill_ld=sld)
+    ops.token_mix_dgrad(B, P, D, t["u"], t["dy"], du, t["w1"], t["ld1"], t["b1"], t["w2"], t["ld2"])
     torch.cuda.synchronize()
     assert torch.isfinite(du).all()
     assert _rel(du, ref["dU"]) <= 4e-3
     assert (du.double() - ref["dU"]).abs().max().item() <= 6e-3 * ref["dU"].abs().max().item()
-    got = spill[:, :, :H].double().transpose(1, 2)
-    assert _rel(got, ref["dZb"]) <= 6e-3
-    # without the spill the result is identical
+    # deterministic: a second launch gives the same bits
     du2 = torch.empty_like(du)
     ops.token_mix_dgrad(B, P, D, t["u"], t["dy"], du2, t["w1"], t["ld1"], t["b1"], t["w2"], t["ld2"])
     torch.cuda.synchronize()
