@@ -852,12 +852,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && (!two || leader)) {
+        // The whole warp runs the loop (all values are warp-uniform, so the descriptors live in uniform registers) and
+        // one elected lane issues the four tcgen05.mma of a k-block back to back.  A single-lane `if (lane == 0)` body
+        // costs ~137 clocks per MMA in R2UR / ELECT overhead (tools/ubench/mma_rate.cu) - more than the 128 clocks a
+        // 128 x 256 x 16 MMA occupies the tensor pipe.
+        if (!two || leader) {
+            uint32_t is_issuer;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_issuer));
+            const bool issuer = is_issuer != 0;
             const uint32_t idesc = make_idesc_bf16(two ? 2 * BM : BM, g.BN, g.a_mn, g.b_mn);
-            const uint32_t a_kstep = g.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
-            const uint32_t b_kstep = g.b_mn ? 2048u : 32u;
-            const uint32_t a_lbo = g.a_mn ? kGroupBytes : 16u;
-            const uint32_t b_lbo = g.b_mn ? kGroupBytes : 16u;
+            const uint32_t idesc2 = make_idesc_bf16(BM, g.BN, g.a2_mn, g.b2_mn);
+            // descriptor templates; the start address (>> 4) is added per instruction, a k-step of 16 advances it by
+            // 32 B (K-major) or 2048 B (MN-major)
+            const uint64_t a_tmpl = make_sdesc_sw128(0u, g.a_mn ? kGroupBytes : 16u, 1024u);
+            const uint64_t b_tmpl = make_sdesc_sw128(0u, g.b_mn ? kGroupBytes : 16u, 1024u);
+            const uint64_t a2_tmpl = make_sdesc_sw128(0u, g.a2_mn ? kGroupBytes : 16u, 1024u);
+            const uint64_t b2_tmpl = make_sdesc_sw128(0u, g.b2_mn ? kGroupBytes : 16u, 1024u);
+            const uint32_t a_ks = g.a_mn ? 128u : 2u, b_ks = g.b_mn ? 128u : 2u;
+            const uint32_t a2_ks = g.a2_mn ? 128u : 2u, b2_ks = g.b2_mn ? 128u : 2u;
             const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int t = work0; t < g.num_tiles; t += work_stride) {
@@ -870,34 +882,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t a_base = tiles_base + stage * g.stage_bytes;
                     const uint32_t b_base = a_base + kABytes;
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024u);
-                        const uint64_t bd = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024u);
-                        if constexpr (TWO) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
-                        else umma_ss(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
-                    }
-                    if (!TWO && g.dual) {
-                        const uint32_t a2_base = a_base + g.pair_bytes, b2_base = a2_base + kABytes;
-                        const uint32_t idesc2 = make_idesc_bf16(BM, g.BN, g.a2_mn, g.b2_mn);
+                    const uint64_t ad = a_tmpl + (a_base >> 4), bd = b_tmpl + (b_base >> 4);
+                    const uint32_t acc0 = kb > tc.kb_begin ? 1u : 0u;
+                    if (issuer) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t ad = make_sdesc_sw128(a2_base + k * (g.a2_mn ? 2048u : 32u), g.a2_mn ? kGroupBytes : 16u, 1024u);
-                            const uint64_t bd = make_sdesc_sw128(b2_base + k * (g.b2_mn ? 2048u : 32u), g.b2_mn ? kGroupBytes : 16u, 1024u);
-                            umma_ss(d_tmem + kDualAccOffset, ad, bd, idesc2, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                            if constexpr (TWO) umma_ss_2cta(d_tmem, ad + k * a_ks, bd + k * b_ks, idesc, k > 0 ? 1u : acc0);
+                            else umma_ss(d_tmem, ad + k * a_ks, bd + k * b_ks, idesc, k > 0 ? 1u : acc0);
                         }
+                        if (!TWO && g.dual) {
+                            const uint32_t a2_base = a_base + g.pair_bytes, b2_base = a2_base + kABytes;
+                            const uint64_t ad2 = a2_tmpl + (a2_base >> 4), bd2 = b2_tmpl + (b2_base >> 4);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_ss(d_tmem + kDualAccOffset, ad2 + k * a2_ks, bd2 + k * b2_ks, idesc2, k > 0 ? 1u : acc0);
+                        }
+                        // the stage is shared through multicast / the pair: release it in every CTA of the cluster
+                        if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&empty_bar[stage]), mc_mask);
+                        else if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
+                        else umma_commit_mc(smem_u32(&empty_bar[stage]), mc_mask);
                     }
-                    // the stage is shared through multicast / the pair: release it in every CTA of the cluster
-                    if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&empty_bar[stage]), mc_mask);
-                    else if (csize == 1) umma_commit(smem_u32(&empty_bar[stage]));
-                    else umma_commit_mc(smem_u32(&empty_bar[stage]), mc_mask);
                     if (++stage == (uint32_t)g.stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&tfull_bar[as]), mc_mask);
-                else umma_commit(smem_u32(&tfull_bar[as]));
+                if (issuer) {
+                    if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&tfull_bar[as]), mc_mask);
+                    else umma_commit(smem_u32(&tfull_bar[as]));
+                }
                 as ^= 1u;
                 if (as == 0) aphase ^= 1u;
             }
