@@ -252,13 +252,35 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
         except Exception:
             pass
+        # second kernel family: the fused token-mixing kernels (HBM bound at 50 / 77 tokens).  Algorithmic bytes per
+        # launch: fwd 10*P*D*B (u bf16 in, x fp32 in, y fp32 out), dgrad 8*P*D*B, wgrad 4*P*D*B
+        tm_roof = None
+        tm = [r for r in recs if r["engine"].startswith("token_mix")]
+        if tm:
+            per = {"token_mix_fwd": (10, 2), "token_mix_dgrad": (8, 3), "token_mix_wgrad": (4, 4)}
+            tm_bytes = sum(per[r["engine"]][0] * r["K"] * r["N"] * (r["batch"] // per[r["engine"]][1]) for r in tm)
+            tm_t = sum(r["ms"] for r in tm) * 1e-3
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            kinds = {}
+            for k in per:
+                rr = [r for r in tm if r["engine"] == k]
+                if rr:
+                    kb = sum(per[k][0] * r["K"] * r["N"] * (r["batch"] // per[k][1]) for r in rr)
+                    kt = sum(r["ms"] for r in rr) * 1e-3
+                    kinds[k] = {"launches": len(rr), "ms": kt * 1e3, "GBps": kb / kt / 1e9}
+            tm_roof = {"bound": "hbm", "kernel": "token_mix_kernel<fwd|dgrad|wgrad> (fused token-mixing MLP, all launches of one step)",
+                       "achieved": tm_bytes / tm_t / 1e9, "peak": hbm, "unit": "GB/s", "frac": tm_bytes / tm_t / 1e9 / hbm,
+                       "launches": len(tm), "ms_per_step": tm_t * 1e3, "algorithmic_MB_per_step": tm_bytes / 1e6,
+                       "tensor_TFLOPs": sum(r["flops"] for r in tm) / tm_t / 1e12, "by_kind": kinds,
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM engine, all launches of one step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per step over the same launches", "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches": len(tc), "gemm_ms_per_step": t_tc * 1e3,
                 "algorithmic_gflop_per_step": fl_tc / 1e9,
                 "channel_mix_only": {"achieved": (sum(r["flops"] for r in big) / t_big / 1e12) if t_big else None,
-                                     "launches": len(big), "ms": t_big * 1e3}}
+                                     "launches": len(big), "ms": t_big * 1e3},
+                "token_mix": tm_roof}
 
     # ---- reductions over ranks ----
     if world > 1:

@@ -186,7 +186,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
 // The fused kernel above keeps serving the gather / class-token variants (3 calls per step).
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                    float* __restrict__ dx, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
@@ -210,16 +210,33 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
     const float invD = 1.0f / D;
     for (long long row = (long long)blockIdx.x * kWarpsPerBlock + warp; row < rows;
          row += (long long)gridDim.x * kWarpsPerBlock) {
-        const float mu = mean[row], rs = rstd[row];
         const float* xr = x + row * (long long)D;
         const float* dyr = dy + row * (long long)D;
-        float4 xh[VPL], d[VPL];
+        const float* rr = dres + row * (long long)D;
+        // every HBM operand of the row is requested before anything is consumed (18 x 16-byte loads in flight per
+        // lane): with the loads interleaved chunk by chunk the kernel paid one DRAM round trip per chunk and sat at
+        // 3.0 TB/s (ncu: all stalls long-scoreboard)
+        float4 xh[VPL], d[VPL], r[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                xh[i] = ld4(xr + c);
+                d[i] = ld4(dyr + c);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            r[i] = (dres != nullptr && c < D) ? ld4(rr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
-                const float4 xv = ld4(xr + c), g = ld4(dyr + c), gm = ld4(gamma + c);
+                const float4 xv = xh[i], g = d[i], gm = ld4(gamma + c);
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 float4 a = ld4(my + c), bsum = ld4(my + W + c);
                 a.x += g.x * xh[i].x; a.y += g.y * xh[i].y; a.z += g.z * xh[i].z; a.w += g.w * xh[i].w;
@@ -240,14 +257,10 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
                 float4 o;
-                o.x = rs * (d[i].x - c1 - xh[i].x * c2);
-                o.y = rs * (d[i].y - c1 - xh[i].y * c2);
-                o.z = rs * (d[i].z - c1 - xh[i].z * c2);
-                o.w = rs * (d[i].w - c1 - xh[i].w * c2);
-                if (dres != nullptr) {
-                    const float4 r = ld4(dres + row * (long long)D + c);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
+                o.x = rs * (d[i].x - c1 - xh[i].x * c2) + r[i].x;
+                o.y = rs * (d[i].y - c1 - xh[i].y * c2) + r[i].y;
+                o.z = rs * (d[i].z - c1 - xh[i].z * c2) + r[i].z;
+                o.w = rs * (d[i].w - c1 - xh[i].w * c2) + r[i].w;
                 st4(dx + row * (long long)D + c, o);
                 if (dx_act != nullptr) st_act4(dx_act, act_dtype, row * (long long)D + c, o);
                 if (want_cs) {
