@@ -40,10 +40,11 @@ namespace mc {
 
 namespace {
 
-constexpr int kE1Warps = 8;
+constexpr int kE1Warps = 12;                                   // three per TMEM lane quarter
 constexpr int kE2Warps = 8;
-constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 640
-constexpr int kProdWarp = 16, kAllocWarp = 17, kMmaWarp = 19;
+constexpr int kE1Groups = kE1Warps / 4;
+constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 768
+constexpr int kProdWarp = kE1Warps + kE2Warps, kAllocWarp = kProdWarp + 1, kInitWarp = kProdWarp + 2, kMmaWarp = kProdWarp + 3;
 constexpr int kMaxAtoms = 5;                                   // hidden width 4P <= 320
 constexpr int kMaxTmStages = 2;
 constexpr uint32_t kAtomBytes = 128 * 128;                     // [128 rows x 64 bf16] swizzled K-major atom
@@ -52,7 +53,7 @@ enum { TM_FWD = 0, TM_DGRAD = 1, TM_WGRAD = 2 };
 
 // Debug timeline (build with -DTM_TRACE, see tools/tokenmix_trace.sh): CTA 0 records (tag, clock) per role.
 #ifdef TM_TRACE
-__device__ unsigned long long g_tm_trace[20][1024];
+__device__ unsigned long long g_tm_trace[24][1024];
 #define TM_TR(role, tag)                                                                                   \
     do {                                                                                                   \
         if (blockIdx.x == 0 && lane == 0 && tr_ctr < 1024)                                                 \
@@ -66,7 +67,11 @@ struct TmArgs {
     int B, P, D, H;
     int Ppad, Hpad, natoms;
     int tiles_d, num_tiles;
-    int SW;                   // hidden columns per pipeline segment (multiple of 64): 128 forward, 64 backward
+    int SW;                   // hidden columns per segment (multiple of 64)
+    int nbuf;                 // working TMEM buffers: 2 = segments ping-pong and the up GEMMs of a tile overlap the E1 pass of
+                              // the previous one; 1 = one buffer (backward: Z and dH side by side leave no room for two)
+    int zpitch;               // TMEM columns between Z and dH inside a working buffer (>= widest segment, multiple of 32)
+    int ybufs;                // output tiles in TMEM (2 forward, 1 dgrad)
     int stages;
     uint32_t grp_bytes;       // Ppad * 128: one [Ppad x 64] swizzled group of an activation / weight tile
     uint32_t a_grp_bytes;     // group pitch of the U tile in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
@@ -138,44 +143,69 @@ __device__ __forceinline__ float2 tm_gelu_grad_from_s(float2 z, float2 s) {
 // which is exactly what TMA's SWIZZLE_128B would produce for a [Ppad x 64] box of a [P x 4P] row-major matrix.
 // Only the hidden slice [jbase, jbase + natoms * 64) is loaded (tile-local column jl = j - jbase).  Called by all
 // threads; contains block-wide barriers.
-__device__ __forceinline__ void load_weight_tiles(const TmArgs& g, uint32_t w1t, uint32_t w2t, int jbase, int natoms) {
-    const int chunks_per_row = natoms * 8;
-    const int total = g.Ppad * chunks_per_row;
-    // w2t[p][jl] = W2[p][jbase + jl]: 16-byte vector loads along j (row pitch and jbase are multiples of 8); w1t zeroed
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-        const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
-        uint32_t v[4] = {0u, 0u, 0u, 0u};
-        if (p < g.P && j < g.H) {
-            const uint4 t = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+constexpr int kWIt = 6;     // per-thread items of a weight pass: ceil(80 * 5 * 8 / 768) = 5
+
+// Phase 1 of the weight staging: every global load of the thread is issued (one DRAM round trip for both matrices).
+__device__ __forceinline__ void issue_weight_loads(const TmArgs& g, int jbase, int natoms, uint4 (&t2)[kWIt], uint4 (&t1)[kWIt]) {
+    const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
+    const int pchunks = g.Ppad / 8, jn = natoms * 64;
+#pragma unroll
+    for (int it = 0; it < kWIt; ++it) {
+        const int idx = threadIdx.x + it * blockDim.x;
+        t2[it] = t1[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (idx < total) {      // w2t[p][jl] = W2[p][jbase + jl]: 16-byte loads along j (pitch and jbase are multiples of 8)
+            const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
+            const int j = jbase + cj * 8;
+            if (p < g.P && j < g.H) t2[it] = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
+        }
+        if (idx < jn * pchunks) {   // w1t[p][jl] = W1[jbase + jl][p]: 16-byte loads along p
+            const int jl = idx / pchunks, pc = idx - jl * pchunks;
+            const int j = jbase + jl, p0 = pc * 8;
+            if (j < g.H && p0 < g.P) t1[it] = *reinterpret_cast<const uint4*>(g.w1 + (long long)j * g.ld1 + p0);
+        }
+    }
+}
+
+// Phase 2: registers -> swizzled shared-memory tiles (W1 is transposed on the way).  Contains a block-wide barrier.
+__device__ __forceinline__ void store_weight_tiles(const TmArgs& g, uint32_t w1t, uint32_t w2t, int jbase, int natoms,
+                                                   const uint4 (&t2)[kWIt], const uint4 (&t1)[kWIt]) {
+    const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
+    const int pchunks = g.Ppad / 8, jn = natoms * 64;
+#pragma unroll
+    for (int it = 0; it < kWIt; ++it) {
+        const int idx = threadIdx.x + it * blockDim.x;
+        if (idx < total) {
+            const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
+            const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
+            uint32_t v[4] = {t2[it].x, t2[it].y, t2[it].z, t2[it].w};
             if (j + 8 > g.H) {   // pad elements of the last chunk are not trusted
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
                     if (j + e >= g.H) v[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
             }
+            const uint32_t off = (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
+            tm_sts128(w2t + off, v[0], v[1], v[2], v[3]);
+            tm_sts128(w1t + off, 0u, 0u, 0u, 0u);
         }
-        const uint32_t off = (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
-        tm_sts128(w2t + off, v[0], v[1], v[2], v[3]);
-        tm_sts128(w1t + off, 0u, 0u, 0u, 0u);
     }
-    __syncthreads();
-    // w1t[p][jl] = W1[jbase + jl][p]: 16-byte vector loads along p, scattered as 2-byte stores (a transpose)
-    const int pchunks = g.Ppad / 8, jn = natoms * 64;
-    for (int idx = threadIdx.x; idx < jn * pchunks; idx += blockDim.x) {
-        const int jl = idx / pchunks, pc = idx - jl * pchunks;
-        const int j = jbase + jl, p0 = pc * 8;
-        if (j < g.H && p0 < g.P) {
-            const uint4 t = *reinterpret_cast<const uint4*>(g.w1 + (long long)j * g.ld1 + p0);
-            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-            const uint32_t cbase = (uint32_t)(jl >> 6) * g.grp_bytes + (uint32_t)(jl & 7) * 2u;
-            const uint32_t c = (uint32_t)((jl & 63) >> 3);
+    __syncthreads();      // the zero fill of w1t is complete
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int p = p0 + e;
-                if (p < g.P) {
-                    const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(w1t + cbase + (uint32_t)p * 128u + ((c ^ (uint32_t)(p & 7)) << 4)), "h"(h) : "memory");
+    for (int it = 0; it < kWIt; ++it) {
+        const int idx = threadIdx.x + it * blockDim.x;
+        if (idx < jn * pchunks) {
+            const int jl = idx / pchunks, pc = idx - jl * pchunks;
+            const int j = jbase + jl, p0 = pc * 8;
+            if (j < g.H && p0 < g.P) {
+                const uint32_t w[4] = {t1[it].x, t1[it].y, t1[it].z, t1[it].w};
+                const uint32_t cbase = (uint32_t)(jl >> 6) * g.grp_bytes + (uint32_t)(jl & 7) * 2u;
+                const uint32_t c = (uint32_t)((jl & 63) >> 3);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int p = p0 + e;
+                    if (p < g.P) {
+                        const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w1t + cbase + (uint32_t)p * 128u + ((c ^ (uint32_t)(p & 7)) << 4)), "h"(h) : "memory");
+                    }
                 }
             }
         }
@@ -202,6 +232,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     [[maybe_unused]] int tr_ctr = 0;
+    if (warp == kInitWarp) TM_TR(kInitWarp, 0);
     const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
     const uint32_t w1t = base + g.off_w1t, w2t = base + g.off_w2t, hbuf = base + g.off_h, h2buf = base + g.off_h2;
     float* b1s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b1);
@@ -218,12 +249,23 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const int my_atoms = (my_hpad + 63) / 64;
     const int nseg = (my_hpad + SW - 1) / SW;
 
+    // ---- prologue: (1) global loads of the resident weights in flight, (2) barriers + TMEM, (3) the first activation
+    //      tiles requested through TMA, (4) weights into their swizzled tiles.  One DRAM round trip in total. ----
+    uint4 wt2[kWIt], wt1[kWIt];
+    issue_weight_loads(g, jbase, my_atoms, wt2, wt1);
+    float b1v[2], b2v = 0.f;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = threadIdx.x + it * blockDim.x;
+        b1v[it] = (i < g.natoms * 64 && jbase + i < g.H) ? g.b1[jbase + i] : 0.f;
+    }
+    if (MODE == TM_FWD && (int)threadIdx.x < g.P) b2v = g.b2[threadIdx.x];
     if (warp == kProdWarp && lane == 0) {
         tma_prefetch_desc(&tmU);
         if (MODE != TM_FWD) tma_prefetch_desc(&tmDY);
         if (MODE == TM_FWD) tma_prefetch_desc(&tmX);
     }
-    if (warp == 18 && lane == 0) {
+    if (warp == kInitWarp && lane == 0) {
         for (int s = 0; s < kMaxTmStages; ++s) {
             mbar_init(smem_u32(&u_full[s]), 1);
             mbar_init(smem_u32(&u_empty[s]), 1);
@@ -235,8 +277,8 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             mbar_init(smem_u32(&y_empty[s]), kE2Warps);
         }
         for (int a = 0; a < kMaxAtoms; ++a) {
-            // an atom whose second 32-column chunk lies beyond the hidden width is written by 4 of the 8 E1 warps
-            mbar_init(smem_u32(&h_full[a]), (my_hpad - a * 64 > 32) ? kE1Warps : kE1Warps / 2);
+            // an atom whose second 32-column chunk lies beyond the hidden width is written by 4 of the 8 chunk owners
+            mbar_init(smem_u32(&h_full[a]), (my_hpad - a * 64 > 32) ? 8 : 4);
             mbar_init(smem_u32(&h_empty[a]), 1);
         }
         fence_mbar_init();
@@ -245,11 +287,37 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         tmem_alloc(smem_u32(&tmem_base_smem), 512);
         tmem_relinquish();
     }
-    // resident operands
-    load_weight_tiles(g, w1t, w2t, jbase, my_atoms);
-    for (int i = threadIdx.x; i < g.natoms * 64; i += blockDim.x) b1s[i] = (jbase + i < g.H) ? g.b1[jbase + i] : 0.f;
-    if (MODE == TM_FWD)
-        for (int i = threadIdx.x; i < g.Ppad; i += blockDim.x) b2s[i] = i < g.P ? g.b2[i] : 0.f;
+    __syncthreads();
+    // activation tile loads: also used by the producer loop below
+    auto issue_tile = [&](int t, uint32_t st) {
+        const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
+        const uint32_t bar = smem_u32(&u_full[st]);
+        const uint32_t dst = base + g.off_stage + st * g.stage_bytes;
+        mbar_arrive_expect_tx(bar, (MODE == TM_FWD ? 2u : 4u) * g.grp_bytes);
+        tma_load_3d(dst, &tmU, bar, d0, 0, b);
+        tma_load_3d(dst + g.a_grp_bytes, &tmU, bar, d0 + 64, 0, b);
+        if (MODE != TM_FWD) {
+            tma_load_3d(dst + 2 * g.a_grp_bytes, &tmDY, bar, d0, 0, b);
+            tma_load_3d(dst + 2 * g.a_grp_bytes + g.grp_bytes, &tmDY, bar, d0 + 64, 0, b);
+        }
+        if (MODE == TM_FWD) {
+            // the fp32 residual tile is read by the E2 warps straight from global memory: pull it into L2 now
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d0 + 32 * i, 0, b);
+        }
+    };
+    int npre = 0;      // tiles requested before the weights are staged (one per smem stage)
+    if (warp == kProdWarp) {
+        for (int t = work0; t < g.num_tiles && npre < g.stages; t += work_stride, ++npre)
+            if (lane == 0) issue_tile(t, (uint32_t)npre);
+    }
+    store_weight_tiles(g, w1t, w2t, jbase, my_atoms, wt2, wt1);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = threadIdx.x + it * blockDim.x;
+        if (i < g.natoms * 64) b1s[i] = b1v[it];
+    }
+    if (MODE == TM_FWD && (int)threadIdx.x < g.Ppad) b2s[threadIdx.x] = b2v;
     if (MODE == TM_WGRAD) {
         // rows Ppad .. 127 of every U group are constant: row Ppad is all ones (its accumulator lane collects
         // db1 = sum_d dZ1), the others zero.  TMA only ever rewrites rows < Ppad of a group.
@@ -268,33 +336,24 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    if (warp == 18) TM_TR(18, 1);
+    if (warp == kInitWarp) TM_TR(kInitWarp, 1);
     // TMEM column map: two rotating working buffers (FWD: Z; else Z and dH side by side), then the output tile(s)
-    const uint32_t wbuf_cols = MODE == TM_FWD ? (uint32_t)SW : 2u * SW;
-    const uint32_t col_y = 2u * wbuf_cols;                                              // FWD: Y0, Y1; DGRAD: dU0, dU1
-    const uint32_t col_acc2 = 2u * wbuf_cols, col_acc1 = 2u * wbuf_cols + g.slice_w;    // WGRAD: dW2 / dW1^T accumulators
+    const uint32_t zpitch = (uint32_t)g.zpitch;
+    const uint32_t wbuf_cols = MODE == TM_FWD ? zpitch : 2u * zpitch;
+    const uint32_t nbuf = (uint32_t)g.nbuf, ybufs = (uint32_t)g.ybufs;
+    const uint32_t col_y = nbuf * wbuf_cols;                                            // FWD: Y0, Y1; DGRAD: dU
+    const uint32_t col_acc2 = nbuf * wbuf_cols, col_acc1 = nbuf * wbuf_cols + g.slice_w;   // WGRAD: dW2 / dW1^T accumulators
 
     if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
-            for (int t = work0; t < g.num_tiles; t += work_stride) {
-                const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
-                mbar_wait_relaxed(smem_u32(&u_empty[st]), ph ^ 1u, 32);
-                TM_TR(kProdWarp, 1);
-                const uint32_t bar = smem_u32(&u_full[st]);
-                const uint32_t dst = base + g.off_stage + st * g.stage_bytes;
-                mbar_arrive_expect_tx(bar, (MODE == TM_FWD ? 2u : 4u) * g.grp_bytes);
-                tma_load_3d(dst, &tmU, bar, d0, 0, b);
-                tma_load_3d(dst + g.a_grp_bytes, &tmU, bar, d0 + 64, 0, b);
-                if (MODE != TM_FWD) {
-                    tma_load_3d(dst + 2 * g.a_grp_bytes, &tmDY, bar, d0, 0, b);
-                    tma_load_3d(dst + 2 * g.a_grp_bytes + g.grp_bytes, &tmDY, bar, d0 + 64, 0, b);
-                }
-                if (MODE == TM_FWD) {
-                    // the fp32 residual tile is read by the E2 warps straight from global memory: pull it into L2 now
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d0 + 32 * i, 0, b);
+            int it = 0;
+            for (int t = work0; t < g.num_tiles; t += work_stride, ++it) {
+                if (it >= npre) {      // the first tiles were requested in the prologue
+                    mbar_wait_relaxed(smem_u32(&u_empty[st]), ph ^ 1u, 32);
+                    TM_TR(kProdWarp, 1);
+                    issue_tile(t, st);
                 }
                 if (++st == (uint32_t)g.stages) {
                     st = 0;
@@ -330,38 +389,39 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 if (a1 > my_atoms) a1 = my_atoms;
                 if (MODE == TM_WGRAD) {
                     // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels)
+                    // one MMA covers the whole hidden slice (N = up to 128 columns = 2 atoms): a tcgen05.mma occupies
+                    // the issue slot for >= 64 clocks whatever its N (tools/ubench/mma_rate.cu)
                     const uint32_t u_base = base + g.off_stage + pst * g.stage_bytes;
                     const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
-                    for (int a = a0; a < a1; ++a) {
-                        mbar_wait(smem_u32(&h_full[a]), pn & 1u);
-                        tc_fence_after();
-                        const int wn = my_hpad - a * 64 < 64 ? my_hpad - a * 64 : 64;
-                        const uint32_t idesc_w = make_idesc_bf16(128, wn, 0, 1);
-                        // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B (+2)
-                        // B (MN-major): K = channel rows of the [128 d x 64 j] atom, 16 rows = 2048 B (+128)
-                        const uint64_t b_h = dMNh + ((hbuf + a * kAtomBytes) >> 4), b_dz = dMNh + ((h2buf + a * kAtomBytes) >> 4);
-                        const uint32_t acc2 = tmem_base + col_acc2 + a * 64, acc1 = tmem_base + col_acc1 + a * 64;
-                        const uint32_t accum0 = pn > 0 ? 1u : 0u;
-                        if (leader) {
+                    for (int a = a0; a < a1; ++a) mbar_wait(smem_u32(&h_full[a]), pn & 1u);
+                    tc_fence_after();
+                    const int c0 = s * SW;
+                    const int wn = my_hpad - c0 < SW ? my_hpad - c0 : SW;
+                    const uint32_t idesc_w = make_idesc_bf16(128, wn, 0, 1);
+                    // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B (+2)
+                    // B (MN-major): K = channel rows of the [128 d x 64 j] atoms, 16 rows = 2048 B (+128); atoms kAtomBytes apart
+                    const uint64_t b_h = dMNh + ((hbuf + a0 * kAtomBytes) >> 4), b_dz = dMNh + ((h2buf + a0 * kAtomBytes) >> 4);
+                    const uint32_t acc2 = tmem_base + col_acc2 + c0, acc1 = tmem_base + col_acc1 + c0;
+                    const uint32_t accum0 = pn > 0 ? 1u : 0u;
+                    if (leader) {
 #pragma unroll
-                            for (int hlf = 0; hlf < 2; ++hlf) {
-                                const uint64_t a_dy = dK + ((dy_base + hlf * g.grp_bytes) >> 4);
-                                const uint64_t a_u = dK + ((u_base + hlf * g.a_grp_bytes) >> 4);
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            const uint64_t a_dy = dK + ((dy_base + hlf * g.grp_bytes) >> 4);
+                            const uint64_t a_u = dK + ((u_base + hlf * g.a_grp_bytes) >> 4);
 #pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    const int ks = hlf * 4 + k4;
-                                    umma_ss(acc2, a_dy + 2 * k4, b_h + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
-                                    umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
-                                }
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const int ks = hlf * 4 + k4;
+                                umma_ss(acc2, a_dy + 2 * k4, b_h + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
+                                umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
                             }
-                            umma_commit(smem_u32(&h_empty[a]));
                         }
+                        for (int a = a0; a < a1; ++a) umma_commit(smem_u32(&h_empty[a]));
+                        if (s == nseg - 1) umma_commit(smem_u32(&u_empty[pst]));
                     }
-                    if (s == nseg - 1 && leader) umma_commit(smem_u32(&u_empty[pst]));
                 } else {
-                    const uint32_t yb = pn & 1u;
+                    const uint32_t yb = ybufs == 2 ? (pn & 1u) : 0u;
                     if (s == 0) {
-                        mbar_wait(smem_u32(&y_empty[yb]), ((pn >> 1) & 1u) ^ 1u);
+                        mbar_wait(smem_u32(&y_empty[yb]), (ybufs == 2 ? ((pn >> 1) & 1u) : (pn & 1u)) ^ 1u);
                         TM_TR(kMmaWarp, 4);
                         tc_fence_after();
                     }
@@ -392,8 +452,9 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 const uint64_t ad_u = dMNa + (u_base >> 4), ad_dy = dMNg + (dy_base >> 4);
                 for (int s = 0; s < nseg; ++s) {
                     // ---- "up" GEMMs of this tile: Z^T = U^T W1^T (and dH^T = dY^T W2) for hidden segment s ----
-                    const uint32_t b = sc & 1u;
-                    mbar_wait(smem_u32(&z_empty[b]), ((sc >> 1) & 1u) ^ 1u);
+                    const uint32_t b = nbuf == 2 ? (sc & 1u) : 0u;
+                    const uint32_t zph = nbuf == 2 ? ((sc >> 1) & 1u) : (sc & 1u);
+                    mbar_wait(smem_u32(&z_empty[b]), zph ^ 1u);
                     TM_TR(kMmaWarp, 3);
                     tc_fence_after();
                     const int c0 = s * SW;
@@ -408,17 +469,29 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                         for (int ks = 0; ks < 5; ++ks) {
                             if (ks < ksteps_up) {
                                 umma_ss(zcol, ad_u + 128 * ks, bd_1 + 128 * ks, idesc_up, ks > 0 ? 1u : 0u);
-                                if (MODE != TM_FWD) umma_ss(zcol + SW, ad_dy + 128 * ks, bd_2 + 128 * ks, idesc_up, ks > 0 ? 1u : 0u);
+                                if (MODE != TM_FWD) umma_ss(zcol + zpitch, ad_dy + 128 * ks, bd_2 + 128 * ks, idesc_up, ks > 0 ? 1u : 0u);
                             }
                         }
                         if (MODE != TM_WGRAD && s == nseg - 1) umma_commit(smem_u32(&u_empty[st]));
                         umma_commit(smem_u32(&z_full[b]));
                     }
+#ifdef TM_TRACE_MMA
+                    TM_TR(kMmaWarp, 6);
+                    mbar_wait(smem_u32(&z_full[b]), zph);     // debug: how long do the up MMAs take to execute?
+                    TM_TR(kMmaWarp, 7);
+#endif
                     ++sc;
-                    // ---- "down" GEMMs of the previous tile, same segment ----
-                    if (have_prev) down_seg(s);
+                    if (nbuf == 2) {
+                        // ---- "down" GEMMs of the previous tile, same segment ----
+                        if (have_prev) down_seg(s);
+                    } else {
+                        // one working buffer: the E1 pass of this segment follows immediately, its atoms feed the down GEMMs
+                        pn = n;
+                        pst = st;
+                        down_seg(s);
+                    }
                 }
-                have_prev = true;
+                have_prev = nbuf == 2;
                 pn = n;
                 pst = st;
                 ++n;
@@ -434,7 +507,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     } else if (warp >= kE2Warps && warp < kE2Warps + kE1Warps) {
         // ===================== E1: hidden activation TMEM -> bf16 smem operand =====================
         const int e = warp - kE2Warps;
-        const int q = e & 3, par = e >> 2;
+        const int q = e & 3, grp = e >> 2;                   // 32-column chunk c of a tile belongs to group c % kE1Groups
         const int r = q * 32 + lane;                         // tile row = channel d0 + r
         const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
@@ -442,17 +515,19 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         uint32_t sc = 0, n = 0;
         for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
             for (int s = 0; s < nseg; ++s, ++sc) {
-                const uint32_t b = sc & 1u;
+                const uint32_t b = nbuf == 2 ? (sc & 1u) : 0u;
                 TM_TR(warp, 1);
-                mbar_wait_relaxed(smem_u32(&z_full[b]), (sc >> 1) & 1u, 20);
+                mbar_wait_relaxed(smem_u32(&z_full[b]), nbuf == 2 ? ((sc >> 1) & 1u) : (sc & 1u), 20);
                 TM_TR(warp, 2);
                 tc_fence_after();
                 const uint32_t zcol = t_lane + b * wbuf_cols;
                 const int a0 = (s * SW) >> 6;
                 int a1 = ((s + 1) * SW) >> 6;
                 if (a1 > my_atoms) a1 = my_atoms;
-                for (int a = a0; a < a1; ++a) {
-                    const int col = a * 64 + par * 32;       // tile-local hidden column of this warp's chunk
+                for (int c = 2 * a0; c < 2 * a1; ++c) {
+                    if (c % kE1Groups != grp) continue;
+                    const int a = c >> 1, par = c & 1;
+                    const int col = c * 32;                  // tile-local hidden column of this warp's chunk
                     const int rel = col - s * SW;
                     if (col < my_hpad) {
                         mbar_wait_relaxed(smem_u32(&h_empty[a]), (n & 1u) ^ 1u, 20);   // the previous tile's down GEMMs released the atom
@@ -479,7 +554,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                             for (int hf = 0; hf < 2; ++hf) {
                                 uint32_t zv[16], dv[16];
                                 tmem_ld16(zcol + rel + hf * 16, zv);
-                                tmem_ld16(zcol + SW + rel + hf * 16, dv);
+                                tmem_ld16(zcol + zpitch + rel + hf * 16, dv);
                                 tmem_ld_wait();
                                 uint32_t o[8], oh[8];
 #pragma unroll
@@ -524,7 +599,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             mbar_wait_relaxed(smem_u32(&y_full[0]), 0u, 64);
             tc_fence_after();
             const int p = r;
-            for (int c = par * 32; c < my_hpad; c += 64) {
+            for (int c = grp * 32; c < my_hpad; c += 32 * kE1Groups) {
                 uint32_t v2[32], v1[32];
                 tmem_ld32(t_lane + col_acc2 + c, v2);
                 tmem_ld32(t_lane + col_acc1 + c, v1);
@@ -572,9 +647,9 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                         }
                     }
                 }
-                const uint32_t yb = n & 1u;
+                const uint32_t yb = ybufs == 2 ? (n & 1u) : 0u;
                 TM_TR(warp, 1);
-                mbar_wait_relaxed(smem_u32(&y_full[yb]), (n >> 1) & 1u, 64);
+                mbar_wait_relaxed(smem_u32(&y_full[yb]), ybufs == 2 ? ((n >> 1) & 1u) : (n & 1u), 64);
                 TM_TR(warp, 2);
                 tc_fence_after();
 #pragma unroll
@@ -618,6 +693,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (warp == kInitWarp) TM_TR(kInitWarp, 9);
     if (warp == kAllocWarp) tmem_dealloc(tmem_base, 512);
 }
 
@@ -666,14 +742,14 @@ int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorM
     MC_CUDA(cudaGetLastError());
 #ifdef TM_TRACE
     {
-        static unsigned long long host[20][1024];
+        static unsigned long long host[24][1024];
         cudaStreamSynchronize(stream);
         cudaMemcpyFromSymbol(host, g_tm_trace, sizeof(host));
         fprintf(stderr, "[tm_trace] mode %d P %d D %d\n", MODE, g.P, g.D);
-        for (int r = 0; r < 20; ++r)
+        for (int r = 0; r < 24; ++r)
             for (int i = 0; i < 1024 && host[r][i] != 0; ++i)
                 fprintf(stderr, "[tm_trace] role %d ev %d tag %llu clk %llu\n", r, i, host[r][i] >> 48, host[r][i] & 0xffffffffffffull);
-        static unsigned long long zero[20][1024];
+        static unsigned long long zero[24][1024];
         cudaMemcpyToSymbol(g_tm_trace, zero, sizeof(zero));
     }
 #endif
@@ -719,9 +795,22 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     int natoms_smem = g.natoms;
     g.slice_w = 128;
     g.nslices = 1;
-    // TMEM: two rotating working buffers (forward 2 x 128 columns of Z; backward 2 x (64 Z + 64 dH)) + 2 output tiles of
-    // Ppad columns, or (wgrad) two 128-column accumulators
-    g.SW = mode == TM_FWD ? 128 : 64;
+    // TMEM plan (512 columns).  A tcgen05.mma costs max(64, N / 2) clocks whatever it computes, so segments are as wide as
+    // the columns allow:  forward  two ping-pong Z buffers of 128 + two output tiles;
+    //                     dgrad    ONE buffer holding Z and dH of a whole segment (all of 4P when it fits) + one output tile;
+    //                     wgrad    Z and dH of the 128-column slice + the two 128-column accumulators.
+    if (mode == TM_FWD) {
+        g.SW = 128; g.nbuf = 2; g.zpitch = 128; g.ybufs = 2;
+    } else if (mode == TM_DGRAD) {
+        g.nbuf = 1; g.ybufs = 1;
+        const int cap = (512 - g.Ppad) / 2;                         // columns available to each of Z, dH
+        g.SW = round_up_i(g.Hpad, 32) <= cap ? round_up_i(g.Hpad, 64) : cap / 64 * 64;
+        const int widest = g.Hpad < g.SW ? g.Hpad : g.SW;
+        g.zpitch = round_up_i(widest, 32);
+    } else {
+        g.SW = 128; g.nbuf = 1; g.zpitch = 128; g.ybufs = 1;
+    }
+    MC_CHECK(g.SW >= 64 && g.SW <= 256, "token_mix: bad segment width");
     if (mode == TM_WGRAD) {
         g.nslices = (g.Hpad + g.slice_w - 1) / g.slice_w;
         natoms_smem = g.slice_w / 64;

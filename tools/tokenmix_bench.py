@@ -44,6 +44,9 @@ def run(B, P, D, iters, nbuf, which):
             fn(i % nbuf)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # park the GPU on a spin kernel while the host enqueues the launches (each costs tens of microseconds of
+        # Python / ctypes / tensor-map encoding): the events then bracket back-to-back kernel execution only
+        torch.cuda._sleep(int(2e7))
         e0.record()
         for i in range(iters):
             fn(i % nbuf)
