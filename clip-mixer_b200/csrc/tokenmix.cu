@@ -44,7 +44,8 @@ constexpr int kE1Warps = 12;                                   // three per TMEM
 constexpr int kE2Warps = 8;
 constexpr int kE1Groups = kE1Warps / 4;
 constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 768
-constexpr int kProdWarp = kE1Warps + kE2Warps, kAllocWarp = kProdWarp + 1, kInitWarp = kProdWarp + 2, kMmaWarp = kProdWarp + 3;
+constexpr int kProdWarp = kE1Warps + kE2Warps, kAllocWarp = kProdWarp + 1, kInitWarp = kAllocWarp, kMmaDnWarp = kProdWarp + 2,
+              kMmaWarp = kProdWarp + 3;
 constexpr int kMaxAtoms = 5;                                   // hidden width 4P <= 320
 constexpr int kMaxTmStages = 2;
 constexpr uint32_t kAtomBytes = 128 * 128;                     // [128 rows x 64 bf16] swizzled K-major atom
@@ -53,7 +54,7 @@ enum { TM_FWD = 0, TM_DGRAD = 1, TM_WGRAD = 2 };
 
 // Debug timeline (build with -DTM_TRACE, see tools/tokenmix_trace.sh): CTA 0 records (tag, clock) per role.
 #ifdef TM_TRACE
-__device__ unsigned long long g_tm_trace[24][1024];
+__device__ unsigned long long g_tm_trace[24][1024];   // indexed by warp
 #define TM_TR(role, tag)                                                                                   \
     do {                                                                                                   \
         if (blockIdx.x == 0 && lane == 0 && tr_ctr < 1024)                                                 \
@@ -119,7 +120,11 @@ __device__ __forceinline__ void tm_tma_prefetch_3d(const CUtensorMap* m, int c0,
 // tanh.approx.f32 runs at the full MUFU rate (16 lanes/clk/SM, measured with tools/ubench/mufu_rate.cu; the packed
 // f16x2 form is split into two MUFU ops and gains nothing).  sigmoid(1.702 z) = 0.5 + 0.5 tanh(0.851 z) costs one
 // MUFU op per element where ex2 + rcp costs two.
+#ifdef TM_FAKE_TANH   // experiment only (wrong results): how fast is the kernel without the MUFU work?
+__device__ __forceinline__ float2 tm_tanh2(float2 a) { return __fmul2_rn(a, make_float2(0.25f, 0.25f)); }
+#else
 __device__ __forceinline__ float2 tm_tanh2(float2 a) { return make_float2(tanh_approx(a.x), tanh_approx(a.y)); }
+#endif
 // QuickGELU (model.py:175-177) on packed pairs: x * sigmoid(1.702 x) = hx + hx * tanh(0.851 x)
 __device__ __forceinline__ float2 tm_gelu2(float2 x) {
     const float2 t = tm_tanh2(__fmul2_rn(x, make_float2(0.851f, 0.851f)));
@@ -143,70 +148,68 @@ __device__ __forceinline__ float2 tm_gelu_grad_from_s(float2 z, float2 s) {
 // which is exactly what TMA's SWIZZLE_128B would produce for a [Ppad x 64] box of a [P x 4P] row-major matrix.
 // Only the hidden slice [jbase, jbase + natoms * 64) is loaded (tile-local column jl = j - jbase).  Called by all
 // threads; contains block-wide barriers.
-constexpr int kWIt = 6;     // per-thread items of a weight pass: ceil(80 * 5 * 8 / 768) = 5
+constexpr int kWIt = 5;     // per-thread 16-byte chunks of a weight tile: ceil(80 * 5 * 8 / 768) = 5
 
-// Phase 1 of the weight staging: every global load of the thread is issued (one DRAM round trip for both matrices).
-__device__ __forceinline__ void issue_weight_loads(const TmArgs& g, int jbase, int natoms, uint4 (&t2)[kWIt], uint4 (&t1)[kWIt]) {
+// Phase 1 of the weight staging: every global load of the thread is issued (one DRAM / L2 round trip for both
+// matrices).  Each thread owns whole 16-byte chunks of the tiles:
+//   w2t[p][jl .. jl+7] = W2[p][jbase + jl ..]   one 16-byte load; consecutive threads walk along j (coalesced)
+//   w1t[p][jl .. jl+7] = W1[jbase + jl + e][p]  eight 2-byte loads; consecutive threads walk along p (coalesced rows of
+//                                               W1, and the 16-byte stores of 8 neighbouring p hit 8 different banks -
+//                                               a scatter of 2-byte stores was 8-16-way bank conflicted: 5 us per launch)
+__device__ __forceinline__ void issue_weight_loads(const TmArgs& g, int jbase, int natoms, uint4 (&t2)[kWIt],
+                                                   unsigned short (&t1)[kWIt][8]) {
     const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
-    const int pchunks = g.Ppad / 8, jn = natoms * 64;
 #pragma unroll
     for (int it = 0; it < kWIt; ++it) {
         const int idx = threadIdx.x + it * blockDim.x;
-        t2[it] = t1[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (idx < total) {      // w2t[p][jl] = W2[p][jbase + jl]: 16-byte loads along j (pitch and jbase are multiples of 8)
-            const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-            const int j = jbase + cj * 8;
-            if (p < g.P && j < g.H) t2[it] = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
-        }
-        if (idx < jn * pchunks) {   // w1t[p][jl] = W1[jbase + jl][p]: 16-byte loads along p
-            const int jl = idx / pchunks, pc = idx - jl * pchunks;
-            const int j = jbase + jl, p0 = pc * 8;
-            if (j < g.H && p0 < g.P) t1[it] = *reinterpret_cast<const uint4*>(g.w1 + (long long)j * g.ld1 + p0);
+        t2[it] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t1[it][e] = 0;
+        if (idx < total) {
+            {
+                const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
+                const int j = jbase + cj * 8;
+                if (p < g.P && j < g.H) t2[it] = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
+            }
+            {
+                const int cj = idx / g.Ppad, p = idx - cj * g.Ppad;
+                const int j = jbase + cj * 8;
+                if (p < g.P) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (j + e < g.H) t1[it][e] = reinterpret_cast<const unsigned short*>(g.w1)[(long long)(j + e) * g.ld1 + p];
+                }
+            }
         }
     }
 }
 
-// Phase 2: registers -> swizzled shared-memory tiles (W1 is transposed on the way).  Contains a block-wide barrier.
+// Phase 2: registers -> swizzled shared-memory tiles, 16-byte stores only.
 __device__ __forceinline__ void store_weight_tiles(const TmArgs& g, uint32_t w1t, uint32_t w2t, int jbase, int natoms,
-                                                   const uint4 (&t2)[kWIt], const uint4 (&t1)[kWIt]) {
+                                                   const uint4 (&t2)[kWIt], const unsigned short (&t1)[kWIt][8]) {
     const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
-    const int pchunks = g.Ppad / 8, jn = natoms * 64;
 #pragma unroll
     for (int it = 0; it < kWIt; ++it) {
         const int idx = threadIdx.x + it * blockDim.x;
         if (idx < total) {
-            const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-            const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
-            uint32_t v[4] = {t2[it].x, t2[it].y, t2[it].z, t2[it].w};
-            if (j + 8 > g.H) {   // pad elements of the last chunk are not trusted
+            {
+                const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
+                const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
+                uint32_t v[4] = {t2[it].x, t2[it].y, t2[it].z, t2[it].w};
+                if (j + 8 > g.H) {   // pad elements of the last chunk are not trusted
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (j + e >= g.H) v[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
-            }
-            const uint32_t off = (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
-            tm_sts128(w2t + off, v[0], v[1], v[2], v[3]);
-            tm_sts128(w1t + off, 0u, 0u, 0u, 0u);
-        }
-    }
-    __syncthreads();      // the zero fill of w1t is complete
-#pragma unroll
-    for (int it = 0; it < kWIt; ++it) {
-        const int idx = threadIdx.x + it * blockDim.x;
-        if (idx < jn * pchunks) {
-            const int jl = idx / pchunks, pc = idx - jl * pchunks;
-            const int j = jbase + jl, p0 = pc * 8;
-            if (j < g.H && p0 < g.P) {
-                const uint32_t w[4] = {t1[it].x, t1[it].y, t1[it].z, t1[it].w};
-                const uint32_t cbase = (uint32_t)(jl >> 6) * g.grp_bytes + (uint32_t)(jl & 7) * 2u;
-                const uint32_t c = (uint32_t)((jl & 63) >> 3);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int p = p0 + e;
-                    if (p < g.P) {
-                        const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w1t + cbase + (uint32_t)p * 128u + ((c ^ (uint32_t)(p & 7)) << 4)), "h"(h) : "memory");
-                    }
+                    for (int e = 0; e < 8; ++e)
+                        if (j + e >= g.H) v[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
                 }
+                tm_sts128(w2t + (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4), v[0], v[1], v[2], v[3]);
+            }
+            {
+                const int cj = idx / g.Ppad, p = idx - cj * g.Ppad;
+                const int grp = cj >> 3, c = cj & 7;
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (uint32_t)t1[it][2 * e] | ((uint32_t)t1[it][2 * e + 1] << 16);
+                tm_sts128(w1t + (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4), v[0], v[1], v[2], v[3]);
             }
         }
     }
@@ -251,7 +254,8 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 
     // ---- prologue: (1) global loads of the resident weights in flight, (2) barriers + TMEM, (3) the first activation
     //      tiles requested through TMA, (4) weights into their swizzled tiles.  One DRAM round trip in total. ----
-    uint4 wt2[kWIt], wt1[kWIt];
+    uint4 wt2[kWIt];
+    unsigned short wt1[kWIt][8];
     issue_weight_loads(g, jbase, my_atoms, wt2, wt1);
     float b1v[2], b2v = 0.f;
 #pragma unroll
@@ -362,86 +366,19 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             }
         }
     } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
-        // Software pipeline over hidden segments: the "up" GEMMs of tile i, segment s are issued right before the
-        // "down" GEMMs of tile i-1, segment s, so the tensor pipe works on tile i while the E1 warps still convert
-        // tile i-1 (the working TMEM buffers rotate per segment, the bf16 operand atoms are released per atom).
-        // The whole warp runs this loop (every value in it is warp-uniform, so descriptors and addresses can live in
-        // uniform registers); one elected lane issues the tcgen05 instructions, in groups of up to 5 per branch.  With a
-        // single-lane `if (lane == 0)` body the compiler spent ~30 instructions (R2UR moves, an ELECT retry loop) per
-        // 32-clock MMA and this one thread paced the whole kernel (-DTM_TRACE timeline).
+        // ===================== MMA issuer, "up" GEMMs: Z^T = U^T W1^T (and dH^T = dY^T W2) =====================
+        // Two issuing warps (this one and kMmaDnWarp) because the kernel is paced by the serial instruction stream of
+        // the issuer: every tcgen05.mma holds the issue slot for >= 64 clocks whatever its N and every barrier wait costs
+        // a few hundred (-DTM_TRACE timeline: one issuer needed ~5700 clocks per tile for 21 MMAs and 9 waits).  A
+        // tcgen05.commit only tracks the MMAs of its own thread, which is exactly the split needed here.
+        // The whole warp runs the loop (all values warp-uniform -> uniform registers); one elected lane issues.
         {
             const bool leader = tm_elect_one();
-            uint32_t st = 0, ph = 0, sc = 0, n = 0;
-            bool have_prev = false;
-            uint32_t pn = 0, pst = 0;
-            const uint32_t idesc_dn = make_idesc_bf16(128, g.Ppad, 0, 0);
-            const uint32_t wdn = MODE == TM_FWD ? w2t : w1t;
+            uint32_t st = 0, ph = 0, sc = 0;
             const int ksteps_up = g.Ppad / 16;    // 1 .. 5
             // descriptor templates: the start-address field (bits 0-13, address >> 4) is added per instruction
-            const uint64_t dK = make_sdesc_sw128(0u, 16u, 1024u);                 // K-major operand
             const uint64_t dMNg = make_sdesc_sw128(0u, g.grp_bytes, 1024u);       // MN-major, 64-wide groups grp_bytes apart
             const uint64_t dMNa = make_sdesc_sw128(0u, g.a_grp_bytes, 1024u);     // MN-major U tile
-            const uint64_t dMNh = make_sdesc_sw128(0u, kAtomBytes, 1024u);        // MN-major view of the H^T / dZ1^T atoms
-            auto down_seg = [&](int s) {
-                const int a0 = (s * SW) >> 6;
-                int a1 = ((s + 1) * SW) >> 6;
-                if (a1 > my_atoms) a1 = my_atoms;
-                if (MODE == TM_WGRAD) {
-                    // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels)
-                    // one MMA covers the whole hidden slice (N = up to 128 columns = 2 atoms): a tcgen05.mma occupies
-                    // the issue slot for >= 64 clocks whatever its N (tools/ubench/mma_rate.cu)
-                    const uint32_t u_base = base + g.off_stage + pst * g.stage_bytes;
-                    const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
-                    for (int a = a0; a < a1; ++a) mbar_wait(smem_u32(&h_full[a]), pn & 1u);
-                    tc_fence_after();
-                    const int c0 = s * SW;
-                    const int wn = my_hpad - c0 < SW ? my_hpad - c0 : SW;
-                    const uint32_t idesc_w = make_idesc_bf16(128, wn, 0, 1);
-                    // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B (+2)
-                    // B (MN-major): K = channel rows of the [128 d x 64 j] atoms, 16 rows = 2048 B (+128); atoms kAtomBytes apart
-                    const uint64_t b_h = dMNh + ((hbuf + a0 * kAtomBytes) >> 4), b_dz = dMNh + ((h2buf + a0 * kAtomBytes) >> 4);
-                    const uint32_t acc2 = tmem_base + col_acc2 + c0, acc1 = tmem_base + col_acc1 + c0;
-                    const uint32_t accum0 = pn > 0 ? 1u : 0u;
-                    if (leader) {
-#pragma unroll
-                        for (int hlf = 0; hlf < 2; ++hlf) {
-                            const uint64_t a_dy = dK + ((dy_base + hlf * g.grp_bytes) >> 4);
-                            const uint64_t a_u = dK + ((u_base + hlf * g.a_grp_bytes) >> 4);
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const int ks = hlf * 4 + k4;
-                                umma_ss(acc2, a_dy + 2 * k4, b_h + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
-                                umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
-                            }
-                        }
-                        for (int a = a0; a < a1; ++a) umma_commit(smem_u32(&h_empty[a]));
-                        if (s == nseg - 1) umma_commit(smem_u32(&u_empty[pst]));
-                    }
-                } else {
-                    const uint32_t yb = ybufs == 2 ? (pn & 1u) : 0u;
-                    if (s == 0) {
-                        mbar_wait(smem_u32(&y_empty[yb]), (ybufs == 2 ? ((pn >> 1) & 1u) : (pn & 1u)) ^ 1u);
-                        TM_TR(kMmaWarp, 4);
-                        tc_fence_after();
-                    }
-                    const uint32_t d_tmem = tmem_base + col_y + yb * g.Ppad;
-                    for (int a = a0; a < a1; ++a) {
-                        mbar_wait(smem_u32(&h_full[a]), pn & 1u);
-                        TM_TR(kMmaWarp, 5);
-                        tc_fence_after();
-                        const int ksteps = (my_hpad - a * 64) >= 64 ? 4 : (my_hpad - a * 64) / 16;
-                        const uint64_t ad = dK + ((hbuf + a * kAtomBytes) >> 4), bd = dK + ((wdn + a * g.grp_bytes) >> 4);
-                        if (leader) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                if (kk < ksteps) umma_ss(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc_dn, (a > 0 || kk > 0) ? 1u : 0u);
-                            umma_commit(smem_u32(&h_empty[a]));
-                            if (a == my_atoms - 1) umma_commit(smem_u32(&y_full[yb]));
-                        }
-                    }
-                }
-            };
             for (int t = work0; t < g.num_tiles; t += work_stride) {
                 TM_TR(kMmaWarp, 1);
                 mbar_wait(smem_u32(&u_full[st]), ph);
@@ -451,7 +388,6 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
                 const uint64_t ad_u = dMNa + (u_base >> 4), ad_dy = dMNg + (dy_base >> 4);
                 for (int s = 0; s < nseg; ++s) {
-                    // ---- "up" GEMMs of this tile: Z^T = U^T W1^T (and dH^T = dY^T W2) for hidden segment s ----
                     const uint32_t b = nbuf == 2 ? (sc & 1u) : 0u;
                     const uint32_t zph = nbuf == 2 ? ((sc >> 1) & 1u) : (sc & 1u);
                     mbar_wait(smem_u32(&z_empty[b]), zph ^ 1u);
@@ -475,33 +411,76 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                         if (MODE != TM_WGRAD && s == nseg - 1) umma_commit(smem_u32(&u_empty[st]));
                         umma_commit(smem_u32(&z_full[b]));
                     }
-#ifdef TM_TRACE_MMA
-                    TM_TR(kMmaWarp, 6);
-                    mbar_wait(smem_u32(&z_full[b]), zph);     // debug: how long do the up MMAs take to execute?
-                    TM_TR(kMmaWarp, 7);
-#endif
                     ++sc;
-                    if (nbuf == 2) {
-                        // ---- "down" GEMMs of the previous tile, same segment ----
-                        if (have_prev) down_seg(s);
-                    } else {
-                        // one working buffer: the E1 pass of this segment follows immediately, its atoms feed the down GEMMs
-                        pn = n;
-                        pst = st;
-                        down_seg(s);
-                    }
                 }
-                have_prev = nbuf == 2;
-                pn = n;
-                pst = st;
-                ++n;
                 if (++st == (uint32_t)g.stages) {
                     st = 0;
                     ph ^= 1u;
                 }
             }
-            if (have_prev)
-                for (int s = 0; s < nseg; ++s) down_seg(s);
+        }
+    } else if (warp == kMmaDnWarp) {
+        // ===================== MMA issuer, "down" GEMMs: consume the bf16 atoms the E1 warps produce =====================
+        {
+            const bool leader = tm_elect_one();
+            uint32_t st = 0, n = 0;
+            const uint32_t idesc_dn = make_idesc_bf16(128, g.Ppad, 0, 0);
+            const uint32_t wdn = MODE == TM_FWD ? w2t : w1t;
+            const uint64_t dK = make_sdesc_sw128(0u, 16u, 1024u);                 // K-major operand
+            const uint64_t dMNh = make_sdesc_sw128(0u, kAtomBytes, 1024u);        // MN-major view of the H^T / dZ1^T atoms
+            for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
+                if (MODE == TM_WGRAD) {
+                    // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels);
+                    // one MMA covers the whole hidden slice (N = up to 128 columns = 2 atoms)
+                    const uint32_t u_base = base + g.off_stage + st * g.stage_bytes;
+                    const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
+                    for (int a = 0; a < my_atoms; ++a) mbar_wait(smem_u32(&h_full[a]), n & 1u);
+                    TM_TR(kMmaDnWarp, 5);
+                    tc_fence_after();
+                    const uint32_t idesc_w = make_idesc_bf16(128, my_hpad, 0, 1);
+                    // A (K-major): rows p, 64-channel atoms = the activation groups; k-step 16 channels = 32 B (+2)
+                    // B (MN-major): K = channel rows of the [128 d x 64 j] atoms, 16 rows = 2048 B (+128); atoms kAtomBytes apart
+                    const uint64_t b_h = dMNh + (hbuf >> 4), b_dz = dMNh + (h2buf >> 4);
+                    const uint32_t acc2 = tmem_base + col_acc2, acc1 = tmem_base + col_acc1;
+                    const uint32_t accum0 = n > 0 ? 1u : 0u;
+                    if (leader) {
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            const uint64_t a_dy = dK + ((dy_base + hlf * g.grp_bytes) >> 4);
+                            const uint64_t a_u = dK + ((u_base + hlf * g.a_grp_bytes) >> 4);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const int ks = hlf * 4 + k4;
+                                umma_ss(acc2, a_dy + 2 * k4, b_h + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
+                                umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
+                            }
+                        }
+                        for (int a = 0; a < my_atoms; ++a) umma_commit(smem_u32(&h_empty[a]));
+                        umma_commit(smem_u32(&u_empty[st]));     // the activation tile is dead once these MMAs have read it
+                    }
+                    if (++st == (uint32_t)g.stages) st = 0;
+                } else {
+                    const uint32_t yb = ybufs == 2 ? (n & 1u) : 0u;
+                    mbar_wait(smem_u32(&y_empty[yb]), (ybufs == 2 ? ((n >> 1) & 1u) : (n & 1u)) ^ 1u);
+                    TM_TR(kMmaDnWarp, 4);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + col_y + yb * g.Ppad;
+                    for (int a = 0; a < my_atoms; ++a) {
+                        mbar_wait(smem_u32(&h_full[a]), n & 1u);
+                        TM_TR(kMmaDnWarp, 5);
+                        tc_fence_after();
+                        const int ksteps = (my_hpad - a * 64) >= 64 ? 4 : (my_hpad - a * 64) / 16;
+                        const uint64_t ad = dK + ((hbuf + a * kAtomBytes) >> 4), bd = dK + ((wdn + a * g.grp_bytes) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (kk < ksteps) umma_ss(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc_dn, (a > 0 || kk > 0) ? 1u : 0u);
+                            umma_commit(smem_u32(&h_empty[a]));
+                            if (a == my_atoms - 1) umma_commit(smem_u32(&y_full[yb]));
+                        }
+                    }
+                }
+            }
             if (MODE == TM_WGRAD && leader) umma_commit(smem_u32(&y_full[0]));   // accumulators final
         }
     } else if (warp >= kE2Warps && warp < kE2Warps + kE1Warps) {
