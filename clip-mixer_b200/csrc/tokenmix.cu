@@ -280,10 +280,13 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             mbar_init(smem_u32(&y_full[s]), 1);
             mbar_init(smem_u32(&y_empty[s]), kE2Warps);
         }
-        for (int a = 0; a < kMaxAtoms; ++a) {
-            // an atom whose second 32-column chunk lies beyond the hidden width is written by 4 of the 8 chunk owners
-            mbar_init(smem_u32(&h_full[a]), (my_hpad - a * 64 > 32) ? 8 : 4);
-            mbar_init(smem_u32(&h_empty[a]), 1);
+        for (int sg = 0; sg < kMaxAtoms; ++sg) {
+            // h_full[sg] / h_empty[sg] hand the bf16 operand atoms of hidden SEGMENT sg between the E1 warps and the
+            // down-GEMM issuer: one arrival per valid 32-column chunk and lane quarter
+            int c_lo = sg * (SW / 32), c_hi = c_lo + SW / 32, nvalid = 0;
+            for (int c = c_lo; c < c_hi; ++c) nvalid += (c * 32 < my_hpad) ? 1 : 0;
+            mbar_init(smem_u32(&h_full[sg]), nvalid > 0 ? 4 * nvalid : 1);
+            mbar_init(smem_u32(&h_empty[sg]), 1);
         }
         fence_mbar_init();
     }
@@ -434,7 +437,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     // one MMA covers the whole hidden slice (N = up to 128 columns = 2 atoms)
                     const uint32_t u_base = base + g.off_stage + st * g.stage_bytes;
                     const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
-                    for (int a = 0; a < my_atoms; ++a) mbar_wait(smem_u32(&h_full[a]), n & 1u);
+                    mbar_wait(smem_u32(&h_full[0]), n & 1u);
                     TM_TR(kMmaDnWarp, 5);
                     tc_fence_after();
                     const uint32_t idesc_w = make_idesc_bf16(128, my_hpad, 0, 1);
@@ -455,7 +458,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                                 umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
                             }
                         }
-                        for (int a = 0; a < my_atoms; ++a) umma_commit(smem_u32(&h_empty[a]));
+                        umma_commit(smem_u32(&h_empty[0]));
                         umma_commit(smem_u32(&u_empty[st]));     // the activation tile is dead once these MMAs have read it
                     }
                     if (++st == (uint32_t)g.stages) st = 0;
@@ -465,18 +468,24 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     TM_TR(kMmaDnWarp, 4);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + col_y + yb * g.Ppad;
-                    for (int a = 0; a < my_atoms; ++a) {
-                        mbar_wait(smem_u32(&h_full[a]), n & 1u);
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        // every barrier wait and every tcgen05.commit costs this thread about as much as an MMA: the
+                        // hand-over is per hidden segment (up to 16 k-steps behind one wait), not per 64-column atom
+                        mbar_wait(smem_u32(&h_full[sg]), n & 1u);
                         TM_TR(kMmaDnWarp, 5);
                         tc_fence_after();
-                        const int ksteps = (my_hpad - a * 64) >= 64 ? 4 : (my_hpad - a * 64) / 16;
-                        const uint64_t ad = dK + ((hbuf + a * kAtomBytes) >> 4), bd = dK + ((wdn + a * g.grp_bytes) >> 4);
+                        const int k0 = sg * (SW / 16);
+                        int k1 = k0 + SW / 16;
+                        if (k1 > my_hpad / 16) k1 = my_hpad / 16;
                         if (leader) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                if (kk < ksteps) umma_ss(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc_dn, (a > 0 || kk > 0) ? 1u : 0u);
-                            umma_commit(smem_u32(&h_empty[a]));
-                            if (a == my_atoms - 1) umma_commit(smem_u32(&y_full[yb]));
+                            for (int ks = k0; ks < k1; ++ks) {
+                                // k-step ks: atom ks / 4 (16 KB apart in the H buffer, grp_bytes apart in the weight tile), 32 B inside
+                                const uint64_t ad = dK + ((hbuf + (uint32_t)(ks >> 2) * kAtomBytes + (uint32_t)(ks & 3) * 32u) >> 4);
+                                const uint64_t bd = dK + ((wdn + (uint32_t)(ks >> 2) * g.grp_bytes + (uint32_t)(ks & 3) * 32u) >> 4);
+                                umma_ss(d_tmem, ad, bd, idesc_dn, ks > 0 ? 1u : 0u);
+                            }
+                            umma_commit(smem_u32(&h_empty[sg]));
+                            if (sg == nseg - 1) umma_commit(smem_u32(&y_full[yb]));
                         }
                     }
                 }
@@ -503,14 +512,15 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 const int a0 = (s * SW) >> 6;
                 int a1 = ((s + 1) * SW) >> 6;
                 if (a1 > my_atoms) a1 = my_atoms;
+                // the down GEMMs of the previous tile have released this segment's operand atoms
+                mbar_wait_relaxed(smem_u32(&h_empty[s]), (n & 1u) ^ 1u, 20);
+                TM_TR(warp, 3);
                 for (int c = 2 * a0; c < 2 * a1; ++c) {
                     if (c % kE1Groups != grp) continue;
                     const int a = c >> 1, par = c & 1;
                     const int col = c * 32;                  // tile-local hidden column of this warp's chunk
                     const int rel = col - s * SW;
                     if (col < my_hpad) {
-                        mbar_wait_relaxed(smem_u32(&h_empty[a]), (n & 1u) ^ 1u, 20);   // the previous tile's down GEMMs released the atom
-                        TM_TR(warp, 3);
                         const uint32_t dst = hbuf + a * kAtomBytes + row_off;
                         if (MODE == TM_FWD) {
                             uint32_t v[32];
@@ -564,7 +574,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&h_full[a]));
+                        if (lane == 0) mbar_arrive(smem_u32(&h_full[s]));
                     }
                 }
                 tc_fence_before();
