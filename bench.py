@@ -247,7 +247,9 @@ def main():
         t_big = sum(r["ms"] for r in big) * 1e-3
         traffic, traffic_src = None, None
         try:   # DRAM bytes of the same launch set (one step), from the committed ncu launch list of this workload
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_gemm_traffic.json")))
+            from clip_mixer_b200.engine import fused_token_mix_enabled
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1s2_gemm_traffic.json" if fused_token_mix_enabled()
+                                             else "r1_final_gemm_traffic.json")))
             if args.model == "B32" and B == 256:
                 traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
         except Exception:
