@@ -24,6 +24,7 @@ struct SimtArgs {
     const float* R; long long ldr, r_bs;
     float* rowsum_out;
     int c_transposed;
+    int splits, k_per_split;   // split-K over blockIdx.z (plain epilogue only): partial sums leave through atomicAdd
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
@@ -47,17 +48,19 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
         const int bb = g.k_spans_batch ? bi : ob;
         const float* Ab = g.A + (long long)bb * g.a_bs;
         const float* Bb = g.B + (long long)bb * g.b_bs;
-        for (int k0 = 0; k0 < g.K; k0 += TK) {
+        const int k_begin = g.splits > 1 ? (int)blockIdx.z * g.k_per_split : 0;
+        const int k_end = g.splits > 1 ? (k_begin + g.k_per_split < g.K ? k_begin + g.k_per_split : g.K) : g.K;
+        for (int k0 = k_begin; k0 < k_end; k0 += TK) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 int r, k;
                 if (g.a_kfast) { k = tid % TK; r = tid / TK + it * 16; } else { r = tid % TM; k = tid / TM + it * 4; }
                 const int gm = m0 + r, gk = k0 + k;
-                As[k][r] = (gm < g.M && gk < g.K) ? Ab[(long long)gm * g.a_sm + (long long)gk * g.a_sk] : 0.f;
+                As[k][r] = (gm < g.M && gk < k_end) ? Ab[(long long)gm * g.a_sm + (long long)gk * g.a_sk] : 0.f;
                 if (g.b_kfast) { k = tid % TK; r = tid / TK + it * 16; } else { r = tid % TN; k = tid / TN + it * 4; }
                 const int gn = n0 + r;
                 const int gk2 = k0 + k;
-                Bs[k][r] = (gn < g.N && gk2 < g.K) ? Bb[(long long)gn * g.b_sn + (long long)gk2 * g.b_sk] : 0.f;
+                Bs[k][r] = (gn < g.N && gk2 < k_end) ? Bb[(long long)gn * g.b_sn + (long long)gk2 * g.b_sk] : 0.f;
             }
             __syncthreads();
 #pragma unroll
@@ -94,7 +97,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
                                          : g.R[(long long)ob * g.r_bs + crow * g.ldr + n];
             float* cp = g.c_transposed ? g.C + (long long)ob * g.c_bs + (long long)n * g.ldc + crow
                                        : g.C + (long long)ob * g.c_bs + crow * g.ldc + n;
-            *cp = g.accumulate ? *cp + x : x;
+            if (g.splits > 1) atomicAdd(cp, x);
+            else *cp = g.accumulate ? *cp + x : x;
             rsum += x;
         }
         if (g.rowsum_out != nullptr) atomicAdd(g.rowsum_out + m, rsum);
@@ -136,7 +140,26 @@ extern "C" int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream_) {
              "gemm: c_transposed excludes zout / zin / row_remap");
     const long long tiles = ceil_div(p->M, TM) * ceil_div(p->N, TN);
     MC_CHECK(tiles < (1ll << 31) && g.out_batch < 65536, "simt gemm: grid too large");
-    dim3 grid((unsigned)tiles, (unsigned)g.out_batch, 1);
+    // The small projection GEMMs (model.py:288,424: 256 x 512 x 768) fill 32 tiles and walk K in 48 dependent
+    // load -> sync -> FMA rounds: split K over blockIdx.z until the grid covers the machine (plain epilogue only).
+    g.splits = 1;
+    g.k_per_split = g.K;
+    const bool plain = p->bias_mode == MC_BIAS_NONE && p->zout == nullptr && p->act == MC_ACT_NONE && p->R == nullptr &&
+                       p->rowsum_out == nullptr && !g.k_spans_batch && g.out_batch == 1 && p->row_remap == 0 &&
+                       !p->c_transposed && (g.accumulate || p->ldc == p->N);
+    if (plain && tiles < 2 * sm_count()) {
+        int sp = (int)ceil_div(2 * sm_count(), tiles);
+        const int max_sp = (int)(g.K / 64);
+        if (sp > max_sp) sp = max_sp;
+        if (sp > 1) {
+            g.k_per_split = (int)(ceil_div(ceil_div(g.K, sp), TK) * TK);
+            g.splits = (int)ceil_div(g.K, g.k_per_split);
+        }
+    }
+    if (g.splits > 1 && !g.accumulate) {
+        MC_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)p->M * (size_t)p->N, stream));
+    }
+    dim3 grid((unsigned)tiles, (unsigned)g.out_batch, (unsigned)g.splits);
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(g);
     MC_CUDA(cudaGetLastError());
     return MC_OK;

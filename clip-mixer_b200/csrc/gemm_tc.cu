@@ -5,11 +5,11 @@
 // residual, training/clip/model.py:206-222; conv1 as im2col GEMM :258,272; projections :288,424;
 // and the dgrad / wgrad GEMMs autograd derives from them, training/training.py:170).
 //
-//   warp 0    : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1    : MMA issuer     (one thread, tcgen05.mma kind::f16, 128 x BN x 16, fp32 accum in TMEM)
-//   warp 2    : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
-//   warps 4-11: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> global,
-//                               256-bit global accesses; two warps per TMEM lane quarter, one per SMSP pair)
+//   warps 0-11: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> swizzled smem -> TMA
+//                               store; three warps per TMEM lane quarter)
+//   warp 12   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warp 14   : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 15   : MMA issuer     (elected lane, tcgen05.mma kind::f16, 128 / 256 x BN x 16, fp32 accum in TMEM)
 //
 // These GEMMs are L2->SM bandwidth bound with a 128 x 256 tile (48 KB of operands per 64-deep k-block
 // against ~42 B/clk/SM of L2 bandwidth), so the kernel runs as 2-CTA clusters along M: the two CTAs
@@ -38,6 +38,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per k-block = 128 B = one swizzle row
 constexpr int kEpiWarps = 12;                    // three per TMEM lane quarter
 constexpr int kThreads = 128 + kEpiWarps * 32;  // 512
+// Warp roles.  The scheduler of an SM sub-partition favours its highest warp id and a polling warp keeps taking issue
+// slots, so the two warps everything else waits for (TMA producer, MMA issuer) sit above the twelve epilogue warps,
+// and the epilogue warps back off with nanosleep while they wait for an accumulator (same finding as in tokenmix.cu).
+constexpr int kAllocWarp = kEpiWarps, kProdWarp = kEpiWarps + 2, kMmaWarp = kEpiWarps + 3;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -724,7 +728,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool two = TWO;              // rank 0 is the leader and issues every MMA
     const bool leader = cta_rank == 0;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kProdWarp && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (g.tma_epi) {
@@ -732,7 +736,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (g.zout != nullptr || g.zin != nullptr || g.R != nullptr) tma_prefetch_desc(&tmZ);
         }
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             // multicast mode: released by the MMA warp of every CTA of the cluster; pair mode: one multicast
@@ -747,7 +751,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < kEpiWarps; ++s) mbar_init(smem_u32(&zin_bar[s]), 1);
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         if constexpr (TWO) {
             tmem_alloc_2cta(smem_u32(&tmem_base_smem), kTmemCols);
             tmem_relinquish_2cta();
@@ -761,7 +765,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 0) {
+    if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -850,7 +854,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         // The whole warp runs the loop (all values are warp-uniform, so the descriptors live in uniform registers) and
         // one elected lane issues the four tcgen05.mma of a k-block back to back.  A single-lane `if (lane == 0)` body
@@ -915,9 +919,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (as == 0) aphase ^= 1u;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < kEpiWarps) {
         // ===================== epilogue =====================
-        const int e = warp - 4;
+        const int e = warp;
         const int q = e & 3;    // TMEM lane quarter == warp id % 4
         const int half = e >> 2;  // which 32-column chunks of every kChunkStride this warp drains (0 .. kEpiWarps/4-1)
         uint32_t as = 0, aphase = 0, zphase = 0;
@@ -941,7 +945,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_arrive_expect_tx(zbar, bytes);
                 tma_load_3d(stage_buf + (EPI == EPI_RESID ? 0u : 2048u), &tmZ, zbar, n0 + half * 32, tc.tm * BM + q * 32, tc.b);
             }
-            mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+            mbar_wait_relaxed(smem_u32(&tfull_bar[as]), aphase, 64);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
             float rsum = 0.f;
@@ -1004,7 +1008,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         if constexpr (TWO) tmem_dealloc_2cta(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
