@@ -58,6 +58,7 @@ _I64, _I32, _F, _P = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 SIGNATURES = {
     "mc_version": [],
     "mc_device_info": [_P, _P, _P],
+    "mc_set_sm_limit": [_I32],
     "mc_gemm_bf16_tc": [C.POINTER(GemmParams), _P],
     "mc_gemm_f32_simt": [C.POINTER(GemmParams), _P],
     "mc_token_mix_supported": [_I64, _I64],

@@ -1,5 +1,6 @@
 // Library-level entry points of the C ABI: version, thread-local error message, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -14,6 +15,12 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Number of SMs the persistent kernels size their grids for.  MC_SM_LIMIT (environment, or mc_set_sm_limit) leaves
+// some SMs to concurrent work: in data-parallel runs the NCCL all-reduce of the gradient buckets needs a few CTAs
+// resident WHILE the backward GEMMs run, and a persistent grid that fills every SM (each CTA takes a whole SM's shared
+// memory) would push the collective into the gaps between kernels.
+static int g_sm_limit = -1;
+
 int sm_count() {
     static int cached = 0;
     if (cached == 0) {
@@ -24,12 +31,23 @@ int sm_count() {
         else
             return 148;  // B200
     }
-    return cached;
+    if (g_sm_limit < 0) {
+        const char* v = getenv("MC_SM_LIMIT");
+        g_sm_limit = v ? atoi(v) : 0;
+    }
+    int n = cached;
+    if (g_sm_limit > 0 && g_sm_limit < n) n = g_sm_limit;
+    return n & ~1;   // CTA pairs: keep it even
 }
 
 }  // namespace mc
 
 extern "C" int mc_version(void) { return 100; }
+
+extern "C" int mc_set_sm_limit(int sms) {
+    mc::g_sm_limit = sms > 0 ? sms : 0;
+    return MC_OK;
+}
 
 extern "C" const char* mc_last_error(void) { return mc::g_last_error; }
 

@@ -44,6 +44,9 @@ extern "C" {
 
 int mc_version(void);
 const char* mc_last_error(void);
+/* Persistent kernels size their grids for min(sms, SM count) SMs (0 = all; also the MC_SM_LIMIT environment variable).
+ * Data-parallel runs leave a few SMs to the NCCL all-reduce that overlaps the backward pass (training.py:93,170). */
+int mc_set_sm_limit(int sms);
 /* sm count / compute capability of the current device */
 int mc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
