@@ -21,11 +21,12 @@
 // "up" GEMMs (N = j, K = p) and as the K-major B operand of the "down" GEMMs (N = p, K = j).
 //
 //   warps 0-7   E2: TMEM -> + residual + bias -> global (forward) / plain store (dgrad)
-//   warps 8-15  E1: TMEM -> bias + QuickGELU (or QuickGELU' product) -> bf16 -> smem operand tile
-//   warp 16     TMA producer: activation tiles (bf16 [P x 128] as two 64-wide swizzled groups) + L2 prefetch of the
+//   warps 8-23  E1: TMEM -> bias + QuickGELU (or QuickGELU' product) -> bf16 -> smem operand tile (32-column chunks
+//               dealt round-robin to four groups of four warps, one warp per TMEM lane quarter)
+//   warp 24     TMA producer: activation tiles (bf16 [P x 128] as two 64-wide swizzled groups) + L2 prefetch of the
 //               fp32 residual tile
-//   warp 17     TMEM allocator
-//   warp 19     MMA issuer (one thread)
+//   warp 25     TMEM allocator, barrier init
+//   warp 26     MMA issuer of the "down" GEMMs      warp 27   MMA issuer of the "up" GEMMs   (one elected lane each)
 //   WGRAD mode: warps 0-7 idle; the weight-gradient accumulators stay in TMEM across all tiles of the CTA.
 // Role order matters: the warp scheduler favours the highest warp id of an SM sub-partition, the MMAs here are tiny
 // (32-64 clocks each), so the kernel is paced by how fast ONE thread gets its tcgen05.mma / commit / try_wait
@@ -40,7 +41,7 @@ namespace mc {
 
 namespace {
 
-constexpr int kE1Warps = 12;                                   // three per TMEM lane quarter
+constexpr int kE1Warps = 16;                                   // four per TMEM lane quarter
 constexpr int kE2Warps = 8;
 constexpr int kE1Groups = kE1Warps / 4;
 constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 768
@@ -54,7 +55,7 @@ enum { TM_FWD = 0, TM_DGRAD = 1, TM_WGRAD = 2 };
 
 // Debug timeline (build with -DTM_TRACE, see tools/tokenmix_trace.sh): CTA 0 records (tag, clock) per role.
 #ifdef TM_TRACE
-__device__ unsigned long long g_tm_trace[24][1024];   // indexed by warp
+__device__ unsigned long long g_tm_trace[28][1024];   // indexed by warp
 #define TM_TR(role, tag)                                                                                   \
     do {                                                                                                   \
         if (blockIdx.x == 0 && lane == 0 && tr_ctr < 1024)                                                 \
@@ -731,14 +732,14 @@ int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorM
     MC_CUDA(cudaGetLastError());
 #ifdef TM_TRACE
     {
-        static unsigned long long host[24][1024];
+        static unsigned long long host[28][1024];
         cudaStreamSynchronize(stream);
         cudaMemcpyFromSymbol(host, g_tm_trace, sizeof(host));
         fprintf(stderr, "[tm_trace] mode %d P %d D %d\n", MODE, g.P, g.D);
-        for (int r = 0; r < 24; ++r)
+        for (int r = 0; r < 28; ++r)
             for (int i = 0; i < 1024 && host[r][i] != 0; ++i)
                 fprintf(stderr, "[tm_trace] role %d ev %d tag %llu clk %llu\n", r, i, host[r][i] >> 48, host[r][i] & 0xffffffffffffull);
-        static unsigned long long zero[24][1024];
+        static unsigned long long zero[28][1024];
         cudaMemcpyToSymbol(g_tm_trace, zero, sizeof(zero));
     }
 #endif
