@@ -303,6 +303,8 @@ def main():
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step * args.steps,
                 "launches_per_step": launches_per_step,
+                "sm_split": {"image_text_sms": stepper.sm_split,
+                             "trials_ms": [[list(c) if c else None, round(t, 3)] for c, t in stepper.sm_split_trials]},
                 "model_flops_utilisation": value / world * TRAIN_GFLOP_PER_SAMPLE * 1e9 / 1e12 /
                 (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)
                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0) if args.model == "B32" else None,

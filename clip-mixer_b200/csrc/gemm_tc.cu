@@ -1190,7 +1190,10 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
             int max_split = 1;
             if (p->split_k > 1) max_split = (int)p->split_k;
             else if (p->split_k == 0 && linear_epi) max_split = 64;
-            for (int sp = (p->split_k > 1 ? max_split : 1); sp <= max_split; sp *= 2) {
+            // any split factor, not only powers of two: 16 tiles x 9 slices fill two rounds of 74 pair slots where
+            // 16 x 4 leaves 10 of them idle and 16 x 8 needs two rounds of longer slices
+            static const int any_split = env_int("MC_GEMM_ANY_SPLIT", 1);
+            for (int sp = (p->split_k > 1 ? max_split : 1); sp <= max_split; sp = any_split ? sp + 1 : sp * 2) {
                 if (sp > g.kb_total) break;
                 double c = model_cost(p->M, p->N, g.out_batch, g.kb_total, bn, sp, sms, heavy, cl);
                 if (sp > 1) c += 800.0;  // atomics
@@ -1325,7 +1328,16 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     if (!g.tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && epi != EPI_ACT_BWD_DUAL && !(g.vec_ok && p->row_remap >= 0))
         epi = EPI_GENERIC;
 
-    const int slots = sms / g.cluster;
+    // Balanced persistent grid (MC_GEMM_BALANCED=1, off by default): the tiles are dealt in ceil(tiles / slots) rounds
+    // whatever the grid, so the launch could take only as many slots as that round count needs (600 tiles on 74 pair
+    // slots = 9 rounds = 67 slots) and leave the other SMs to the other streams.  Measured neutral on the two-stream
+    // step (15.89 vs 15.94 ms) and slower together with the SM split (15.5 vs 15.0 ms), hence opt-in.
+    static const int balanced = env_int("MC_GEMM_BALANCED", 0);
+    int slots = sms / g.cluster;
+    if (balanced && g.num_tiles > slots) {
+        const int rounds = (g.num_tiles + slots - 1) / slots;
+        slots = (g.num_tiles + rounds - 1) / rounds;
+    }
     const int grid = (g.num_tiles < slots ? g.num_tiles : slots) * g.cluster;
     static const int debug = env_int("MC_GEMM_DEBUG", 0);
     if (debug)

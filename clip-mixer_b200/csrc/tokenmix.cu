@@ -33,6 +33,7 @@
 // instructions issued (measured with the -DTM_TRACE timeline: with the MMA issuer as warp 1 below sixteen polling
 // epilogue warps it needed ~1000 clocks per four MMAs).  Waiting epilogue warps back off with nanosleep.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -782,6 +783,13 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
 
     const int sms = sm_count();
     int grid = g.num_tiles < sms ? g.num_tiles : sms;
+    {   // balanced persistent grid (same rule as csrc/gemm_tc.cu): only as many CTAs as the round count needs
+        const char* bal = getenv("MC_GEMM_BALANCED");
+        if (bal != nullptr && atoi(bal) != 0 && g.num_tiles > sms) {
+            const int rounds = (g.num_tiles + sms - 1) / sms;
+            grid = (g.num_tiles + rounds - 1) / rounds;
+        }
+    }
     int natoms_smem = g.natoms;
     g.slice_w = 128;
     g.nslices = 1;

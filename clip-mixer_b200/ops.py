@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_NONE, F32, MAJOR_K, MAJOR_MN,
                    GemmParams, MixerClipError, TokenMixParams, check)
 
-__all__ = ["gemm", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
+__all__ = ["gemm", "set_sm_limit", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
            "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "adamw", "device_info",
            "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
            "ACT_GELU_BWD", "launch_count", "reset_launch_count", "enable_gemm_timing", "collect_gemm_timing"]
@@ -77,6 +77,11 @@ def dtype_code(t: torch.Tensor) -> int:
         return _DT[t.dtype]
     except KeyError:
         raise MixerClipError(f"unsupported dtype {t.dtype}") from None
+
+
+def set_sm_limit(sms: int):
+    """Persistent kernels launched after this call size their grids for ``sms`` SMs (0 = all): mc_set_sm_limit."""
+    check(_lib.load().mc_set_sm_limit(int(sms)), "mc_set_sm_limit")
 
 
 def device_info():

@@ -54,6 +54,25 @@ class FusedTrainStep:
         self._side = None
         self.overlap_towers = overlap_towers
         self.micro_batch = micro_batch
+        # SM split: while the two towers run on two streams, each tower's persistent kernels are sized for its own
+        # share of the SMs, so a tensor-bound GEMM of one tower runs beside an HBM-bound row kernel of the other
+        # instead of each taking turns on the whole GPU (every kernel of this step holds a full SM per CTA).
+        # MC_SM_SPLIT = "image_sms,text_sms" fixes the shares, "off" sizes every kernel for all SMs, "auto" (default,
+        # CUDA-graph mode only) times a few shares around the towers' FLOP ratio at capture and keeps the fastest.
+        split = os.environ.get("MC_SM_SPLIT", "auto").strip().lower()
+        self.sm_split = None
+        self.sm_split_auto = False
+        if split == "auto":
+            self.sm_split_auto = True
+        elif split not in ("", "off", "0", "none"):
+            self.sm_split = tuple(int(v) for v in split.split(","))
+            if len(self.sm_split) != 2 or min(self.sm_split) < 2:
+                raise MixerClipError(f"MC_SM_SPLIT={split!r}: expected 'image_sms,text_sms', 'auto' or 'off'")
+        self.sm_split_trials = []
+
+    def _tower_sms(self, which: int):
+        if self.sm_split is not None and self.overlap_towers:
+            ops.set_sm_limit(self.sm_split[which])
 
     def _side_stream(self):
         if not self.overlap_towers:
@@ -86,9 +105,12 @@ class FusedTrainStep:
         fork = torch.cuda.Event()
         fork.record(main)
         side.wait_event(fork)
+        self._tower_sms(1)
         with torch.cuda.stream(side):
             ws_t = txt_t.forward(texts, prec, True)                                 # model(images, texts)   :156
+        self._tower_sms(0)
         ws_i = img_t.forward(images, prec, True)
+        ops.set_sm_limit(0)
         main.wait_stream(side)
         if self.dp is not None and self.world > 1:
             ui_all, ut_all = self.dp.gather(ws_i.u_feat, ws_t.u_feat)               # accelerator.gather     :158-159
@@ -109,9 +131,12 @@ class FusedTrainStep:
         fork2 = torch.cuda.Event()
         fork2.record(main)
         side.wait_event(fork2)
+        self._tower_sms(1)
         with torch.cuda.stream(side):
             txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)                # accelerator.backward   :170
+        self._tower_sms(0)
         img_t.backward(ws_i, b["dui"], prec, after_block=hook_i)
+        ops.set_sm_limit(0)
         main.wait_stream(side)
         self._finish_step()
 
@@ -207,9 +232,63 @@ class FusedTrainStep:
         if self.model._precision.act == torch.bfloat16:
             self.store.refresh_mirror(force=True)
         self.model._trusted_mirror = True     # do not bake a redundant cast pass into the graph
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._device_step(self.static_images, self.static_texts)
+        candidates = self._split_candidates(images.shape[0])
+        graphs = []
+        for cand in candidates:
+            self.sm_split = cand
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._device_step(self.static_images, self.static_texts)
+            graphs.append(graph)
+        pick = 0
+        if len(candidates) > 1:
+            # Interleaved timing (blocks of replays alternate over the candidates, so clock / power drift hits all of
+            # them alike: back-to-back blocks of one candidate differ by more than the candidates do).  The replays are
+            # real optimizer steps, so the state is put back afterwards.
+            total = [0.0] * len(candidates)
+            for _ in range(3):
+                for i, graph in enumerate(graphs):
+                    total[i] += self._time_graph(graph)
+            self.sm_split_trials = [(c, t / 3) for c, t in zip(candidates, total)]
+            pick = min(range(len(candidates)), key=lambda i: total[i])
+            self.store.flat_p.copy_(snap_p)
+            self.opt.m.copy_(snap_m)
+            self.opt.v.copy_(snap_v)
+            if self.model._precision.act == torch.bfloat16:
+                self.store.refresh_mirror(force=True)
+            self.model._trusted_mirror = True
+        self.sm_split, self.graph = candidates[pick], graphs[pick]
+
+    def _split_candidates(self, n):
+        """SM shares (image, text) to try at capture; [None] = no split."""
+        if not (self.sm_split_auto and self.overlap_towers) or (self.micro_batch is not None and n > self.micro_batch):
+            return [self.sm_split]
+        sms = ops.device_info()[0]
+        work = []
+        for t in (self.model._towers["image"], self.model._towers["text"]):
+            work.append(t.L * (16.0 * t.P * t.D * t.D + 16.0 * t.P * t.P * t.D))   # mixer GEMM FLOPs per sample (SURVEY 8-a3/a4)
+        centre = int(round(sms * work[0] / (work[0] + work[1]) / 2.0)) * 2
+        cands = [None]
+        for d in (-6, -4, -2, 0):       # measured optimum sits a little below the FLOP share (B/32: 82-84 of 148 vs 86)
+            a = centre + d
+            if 8 <= a <= sms - 8:
+                cands.append((a, sms - a))
+        return cands
+
+    def _time_graph(self, graph, reps: int = 6) -> float:
+        """Milliseconds per replay (max over ranks, so every rank keeps the same candidate)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.store.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
 
 
 # -------------------------------------------------------------------------------------------------
