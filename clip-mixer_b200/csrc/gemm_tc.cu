@@ -8,7 +8,8 @@
 //   warps 0-11: epilogue       (tcgen05.ld 32x32b -> bias / QuickGELU / QuickGELU' / residual -> swizzled smem -> TMA
 //                               store; three warps per TMEM lane quarter)
 //   warp 12   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
-//   warp 14   : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 14   : TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx; elected lane)
+//   warp 13   : second TMA producer (B operand) when prod2
 //   warp 15   : MMA issuer     (elected lane, tcgen05.mma kind::f16, 128 / 256 x BN x 16, fp32 accum in TMEM)
 //
 // These GEMMs are L2->SM bandwidth bound with a 128 x 256 tile (48 KB of operands per 64-deep k-block
@@ -41,7 +42,7 @@ constexpr int kThreads = 128 + kEpiWarps * 32;  // 512
 // Warp roles.  The scheduler of an SM sub-partition favours its highest warp id and a polling warp keeps taking issue
 // slots, so the two warps everything else waits for (TMA producer, MMA issuer) sit above the twelve epilogue warps,
 // and the epilogue warps back off with nanosleep while they wait for an accumulator (same finding as in tokenmix.cu).
-constexpr int kAllocWarp = kEpiWarps, kProdWarp = kEpiWarps + 2, kMmaWarp = kEpiWarps + 3;
+constexpr int kAllocWarp = kEpiWarps, kProdWarpB = kEpiWarps + 1, kProdWarp = kEpiWarps + 2, kMmaWarp = kEpiWarps + 3;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -57,6 +58,7 @@ struct GemmTcArgs {
     int cluster, tiles_m_eff, b_box_rows;   // cluster: CTAs per cluster along M (1 or 2)
     int tma_epi;                            // outputs leave through smem staging + TMA store
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
+    int prod2;                              // second producer warp issues the B operand
     int epi_smem_off;                       // byte offset of the epilogue staging area from tiles_base
     // epilogue
     void* C;
@@ -765,92 +767,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == kProdWarp) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
-            for (int t = work0; t < g.num_tiles; t += work_stride) {
-                const TileCoord tc = decode_tile(g, t, cta_rank);
-                const int m0 = tc.tm * BM, n0 = tc.tn * g.BN;
-                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
-                    int bb = tc.b, kk = kb * BK;
-                    if (g.k_spans_batch) {
-                        bb = kb / g.kb_per_batch;
-                        kk = (kb - bb * g.kb_per_batch) * BK;
-                    }
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-                    const uint32_t bar = smem_u32(&full_bar[stage]);
-                    const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
-                    const uint32_t b_dst = a_dst + kABytes;
-                    const int ba = g.a_batched ? bb : 0, bbt = g.b_batched ? bb : 0;
+    if (warp == kProdWarp || (warp == kProdWarpB && g.prod2)) {
+        // ===================== TMA producer(s) =====================
+        // Like the MMA issuer, the whole warp runs the loop on warp-uniform values and one elected lane issues: a
+        // single-lane `if (lane == 0)` body makes the compiler wrap every UTMALDG in an ELECT / R2UR.BROADCAST /
+        // BRA.U.ANY waterfall, and the ncu source view of the r1s2 kernels showed the producer busy issuing all the time
+        // (almost never waiting for a free stage) while the MMA warp waited for data 43 % of its time - ~1200 clocks per
+        // k-block against 512 of MMA work.  With prod2 the (otherwise idle) second producer warp issues the B operand
+        // while this one issues A; both watch the same empty barrier, the A warp posts the expected byte count (bytes
+        // that complete before the expect_tx only make the transaction count dip below zero, the phase cannot flip
+        // before the arrival).
+        const bool do_a = warp == kProdWarp;
+        const bool do_b = g.prod2 ? warp == kProdWarpB : true;
+        uint32_t is_issuer;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_issuer));
+        const bool issuer = is_issuer != 0;
+        uint32_t stage = 0, phase = 0;
+        const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
+        for (int t = work0; t < g.num_tiles; t += work_stride) {
+            const TileCoord tc = decode_tile(g, t, cta_rank);
+            const int m0 = tc.tm * BM, n0 = tc.tn * g.BN;
+            for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                int bb = tc.b, kk = kb * BK;
+                if (g.k_spans_batch) {
+                    bb = kb / g.kb_per_batch;
+                    kk = (kb - bb * g.kb_per_batch) * BK;
+                }
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                const uint32_t bar = smem_u32(&full_bar[stage]);
+                const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
+                const uint32_t b_dst = a_dst + kABytes;
+                const int ba = g.a_batched ? bb : 0, bbt = g.b_batched ? bb : 0;
+                if (issuer) {
                     if constexpr (TWO) {
                         // pair mode: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
                         const uint32_t lbar = leader ? bar : mapa_u32(bar, 0);
-                        if (leader) mbar_arrive_expect_tx(bar, 2u * (kABytes + g.b_tx_bytes));
-                        if (g.a_mn) {
-                            tma_load_3d_2sm(a_dst, &tmA, lbar, m0, kk, ba);
-                            tma_load_3d_2sm(a_dst + kGroupBytes, &tmA, lbar, m0 + 64, kk, ba);
-                        } else {
-                            tma_load_3d_2sm(a_dst, &tmA, lbar, kk, m0, ba);
+                        if (do_a) {
+                            if (leader) mbar_arrive_expect_tx(bar, 2u * (kABytes + g.b_tx_bytes));
+                            if (g.a_mn) {
+                                tma_load_3d_2sm(a_dst, &tmA, lbar, m0, kk, ba);
+                                tma_load_3d_2sm(a_dst + kGroupBytes, &tmA, lbar, m0 + 64, kk, ba);
+                            } else {
+                                tma_load_3d_2sm(a_dst, &tmA, lbar, kk, m0, ba);
+                            }
                         }
-                        const int nh = n0 + cta_rank * (g.BN / 2);   // this CTA supplies half of the B tile's columns
-                        if (g.b_mn) {
-                            for (int j = 0; j * 64 < g.BN / 2; ++j)
-                                tma_load_3d_2sm(b_dst + j * kGroupBytes, &tmB, lbar, nh + j * 64, kk, bbt);
-                        } else {
-                            tma_load_3d_2sm(b_dst, &tmB, lbar, kk, nh, bbt);
-                        }
-                        if (++stage == (uint32_t)g.stages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(bar, (g.dual ? 2u : 1u) * (kABytes + g.b_tx_bytes));
-                    if (g.a_mn) {
-                        tma_load_3d(a_dst, &tmA, bar, m0, kk, ba);
-                        tma_load_3d(a_dst + kGroupBytes, &tmA, bar, m0 + 64, kk, ba);
-                    } else {
-                        tma_load_3d(a_dst, &tmA, bar, kk, m0, ba);
-                    }
-                    if (g.dual) {   // second operand pair of the same tile (single-CTA mode only)
-                        const uint32_t a2_dst = a_dst + g.pair_bytes, b2_dst = a2_dst + kABytes;
-                        const int ba2 = g.a2_batched ? bb : 0, bb2 = g.b2_batched ? bb : 0;
-                        if (g.a2_mn) {
-                            tma_load_3d(a2_dst, &tmA2, bar, m0, kk, ba2);
-                            tma_load_3d(a2_dst + kGroupBytes, &tmA2, bar, m0 + 64, kk, ba2);
-                        } else {
-                            tma_load_3d(a2_dst, &tmA2, bar, kk, m0, ba2);
-                        }
-                        if (g.b2_mn) {
-                            for (int j = 0; j * 64 < g.BN; ++j)
-                                tma_load_3d(b2_dst + j * kGroupBytes, &tmB2, bar, n0 + j * 64, kk, bb2);
-                        } else {
-                            tma_load_3d(b2_dst, &tmB2, bar, kk, n0, bb2);
-                        }
-                    }
-                    if (csize == 1) {
-                        if (g.b_mn) {
-                            for (int j = 0; j * 64 < g.BN; ++j)
-                                tma_load_3d(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt);
-                        } else {
-                            tma_load_3d(b_dst, &tmB, bar, kk, n0, bbt);
+                        if (do_b) {
+                            const int nh = n0 + cta_rank * (g.BN / 2);   // this CTA supplies half of the B tile's columns
+                            if (g.b_mn) {
+                                for (int j = 0; j * 64 < g.BN / 2; ++j)
+                                    tma_load_3d_2sm(b_dst + j * kGroupBytes, &tmB, lbar, nh + j * 64, kk, bbt);
+                            } else {
+                                tma_load_3d_2sm(b_dst, &tmB, lbar, kk, nh, bbt);
+                            }
                         }
                     } else {
-                        // this CTA fetches its share of the B tile and multicasts it to the whole cluster
-                        if (g.b_mn) {
-                            for (int j = cta_rank; j * 64 < g.BN; j += csize)
-                                tma_load_3d_mc(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt, mc_mask);
-                        } else {
-                            const int r0 = cta_rank * g.b_box_rows;
-                            tma_load_3d_mc(b_dst + r0 * (BK * 2), &tmB, bar, kk, n0 + r0, bbt, mc_mask);
+                        if (do_a) {
+                            mbar_arrive_expect_tx(bar, (g.dual ? 2u : 1u) * (kABytes + g.b_tx_bytes));
+                            if (g.a_mn) {
+                                tma_load_3d(a_dst, &tmA, bar, m0, kk, ba);
+                                tma_load_3d(a_dst + kGroupBytes, &tmA, bar, m0 + 64, kk, ba);
+                            } else {
+                                tma_load_3d(a_dst, &tmA, bar, kk, m0, ba);
+                            }
+                            if (g.dual) {   // second operand pair of the same tile (single-CTA mode only)
+                                const uint32_t a2_dst = a_dst + g.pair_bytes, b2_dst = a2_dst + kABytes;
+                                const int ba2 = g.a2_batched ? bb : 0, bb2 = g.b2_batched ? bb : 0;
+                                if (g.a2_mn) {
+                                    tma_load_3d(a2_dst, &tmA2, bar, m0, kk, ba2);
+                                    tma_load_3d(a2_dst + kGroupBytes, &tmA2, bar, m0 + 64, kk, ba2);
+                                } else {
+                                    tma_load_3d(a2_dst, &tmA2, bar, kk, m0, ba2);
+                                }
+                                if (g.b2_mn) {
+                                    for (int j = 0; j * 64 < g.BN; ++j)
+                                        tma_load_3d(b2_dst + j * kGroupBytes, &tmB2, bar, n0 + j * 64, kk, bb2);
+                                } else {
+                                    tma_load_3d(b2_dst, &tmB2, bar, kk, n0, bb2);
+                                }
+                            }
+                        }
+                        if (do_b) {
+                            if (csize == 1) {
+                                if (g.b_mn) {
+                                    for (int j = 0; j * 64 < g.BN; ++j)
+                                        tma_load_3d(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt);
+                                } else {
+                                    tma_load_3d(b_dst, &tmB, bar, kk, n0, bbt);
+                                }
+                            } else {
+                                // this CTA fetches its share of the B tile and multicasts it to the whole cluster
+                                if (g.b_mn) {
+                                    for (int j = cta_rank; j * 64 < g.BN; j += csize)
+                                        tma_load_3d_mc(b_dst + j * kGroupBytes, &tmB, bar, n0 + j * 64, kk, bbt, mc_mask);
+                                } else {
+                                    const int r0 = cta_rank * g.b_box_rows;
+                                    tma_load_3d_mc(b_dst + r0 * (BK * 2), &tmB, bar, kk, n0 + r0, bbt, mc_mask);
+                                }
+                            }
                         }
                     }
-                    if (++stage == (uint32_t)g.stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                }
+                if (++stage == (uint32_t)g.stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
@@ -1222,6 +1241,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     static const int allow_2cta = env_int("MC_GEMM_2CTA", 1);
     g.two_cta = (allow_2cta && g.cluster == 2 && g.BN % 32 == 0 && (!g.b_mn || g.BN % 128 == 0)) ? 1 : 0;
     g.b_box_rows = g.BN / g.cluster;
+    static const int prod2 = env_int("MC_GEMM_PROD2", 1);
+    g.prod2 = prod2 ? 1 : 0;
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
     const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;
     g.b_tx_bytes = g.b_mn ? (int)(ceil_div(bn_cta, 64) * kGroupBytes) : bn_cta * BK * 2;
