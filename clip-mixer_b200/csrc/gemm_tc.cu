@@ -59,6 +59,8 @@ struct GemmTcArgs {
     int tma_epi;                            // outputs leave through smem staging + TMA store
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
+    int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
+    int dbg_skip;                           // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue
     int epi_smem_off;                       // byte offset of the epilogue staging area from tiles_base
     // epilogue
     void* C;
@@ -275,7 +277,19 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
     const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
     return __ffma2_rn(hx, t, hx);
 }
+#ifndef MC_GELU_GRAD_TANH
+#define MC_GELU_GRAD_TANH 1
+#endif
 __device__ __forceinline__ float2 gelu_grad2(float2 z) {
+#if MC_GELU_GRAD_TANH
+    // sigmoid(1.702 z) = 0.5 + 0.5 tanh(0.851 z): ONE MUFU op per element instead of two (ex2 + rcp).  The GELU-backward
+    // epilogue is the slowest of the engine (64 us on its own for the B/32 dZ2 tile set, MC_GEMM_DEBUG_SKIP=3) and two
+    // MUFU ops per element are 4096 clocks per 128 x 256 tile - the whole MMA time of a K = 512 tile.  tanh.approx is
+    // good to 2^-11 relative: 1e-4 absolute on g', against the 2e-3 of the bf16 rounding of the result.
+    const float2 a = __fmul2_rn(z, make_float2(0.851f, 0.851f));
+    const float2 t = make_float2(tanh_approx(a.x), tanh_approx(a.y));
+    const float2 s = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+#else
     const float2 a = __fmul2_rn(z, make_float2(-2.4554669595930157f, -2.4554669595930157f));   // -1.702*log2(e)*z
     float ex, ey, sx, sy;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a.x));
@@ -284,6 +298,7 @@ __device__ __forceinline__ float2 gelu_grad2(float2 z) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sx) : "f"(den.x));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sy) : "f"(den.y));
     const float2 s = make_float2(sx, sy);
+#endif
     const float2 w = __fmul2_rn(z, make_float2(kGeluA, kGeluA));
     const float2 nw = __fmul2_rn(z, make_float2(-kGeluA, -kGeluA));
     const float2 t1 = __ffma2_rn(nw, s, w);      // w (1 - s)
@@ -454,7 +469,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 constexpr int kChunkStride = 32 * (kEpiWarps / 4);   // columns between consecutive chunks of one epilogue warp
-constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C chunk (2 KB) + an fp16 Z chunk (2 KB)
+constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C chunk (2 KB) + an fp16 Z chunk (2 KB); +2 KB per extra Z slot
 
 // One 32-column chunk leaving through shared memory and a TMA store: every lane owns one output row, writes it
 // into a swizzled staging tile (conflict-free 16-byte stores), and one lane hands the [32 x 32] box to the TMA
@@ -465,7 +480,7 @@ template <int EPI>
 __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
                                                uint32_t taddr, uint32_t stage, float bias_m, bool row_ok, long long crow,
                                                int m_base, int b, int n, int lane, uint32_t zbar, uint32_t zphase,
-                                               int next_n, float& rsum) {
+                                               uint32_t zoff, int pf_n, int pf_m, int pf_b, float& rsum) {
     uint32_t v[32];
     [[maybe_unused]] const bool full = n + 32 <= g.N;
     if constexpr (EPI == EPI_ACT_BWD_DUAL) {
@@ -497,8 +512,9 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             bulk_commit();
         }
     } else if constexpr (EPI == EPI_ACT_BWD) {
-        // The saved pre-activation chunk (fp16 [32 x 32], swizzle-64B) was requested by TMA one chunk ahead into
-        // the second half of the staging tile (see the epilogue loop); rows >= M / columns >= N arrive as zeros.
+        // The saved pre-activation chunk (fp16 [32 x 32], swizzle-64B) was requested by TMA one or two chunks ahead
+        // (across tile boundaries, see the epilogue loop) into slot `zoff` of the staging area; rows >= M / columns
+        // >= N arrive as zeros.  The slot is handed to the next outstanding request (pf_*) as soon as it has been read.
         mbar_wait(zbar, zphase);
         const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
         uint32_t z[16];
@@ -506,11 +522,11 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
         for (int j = 0; j < 4; ++j)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(z[4 * j]), "=r"(z[4 * j + 1]), "=r"(z[4 * j + 2]), "=r"(z[4 * j + 3])
-                         : "r"(rowp + 2048 + ((j ^ sw) << 4)));
+                         : "r"(rowp + zoff + ((j ^ sw) << 4)));
         __syncwarp();
-        if (lane == 0 && next_n >= 0) {   // prefetch the next chunk's pre-activations
+        if (lane == 0 && pf_n >= 0) {
             mbar_arrive_expect_tx(zbar, 2048);
-            tma_load_3d(stage + 2048, tmZ, zbar, next_n, m_base, b);
+            tma_load_3d(stage + zoff, tmZ, zbar, pf_n, pf_m, pf_b);
         }
         tmem_ld32(taddr, v);
         tmem_ld_wait();
@@ -595,9 +611,9 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
                          : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
                          : "r"(rowp + ((j ^ sw) << 4)));
         __syncwarp();
-        if (lane == 0 && next_n >= 0) {
+        if (lane == 0 && pf_n >= 0) {
             mbar_arrive_expect_tx(zbar, 4096);
-            tma_load_3d(stage, tmZ, zbar, next_n, m_base, b);
+            tma_load_3d(stage, tmZ, zbar, pf_n, pf_m, pf_b);
         }
         tmem_ld32(taddr, v);
         tmem_ld_wait();
@@ -716,7 +732,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
-    __shared__ __align__(8) uint64_t zin_bar[kEpiWarps];
+    __shared__ __align__(8) uint64_t zin_bar[kEpiWarps][2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
@@ -750,7 +766,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // pair mode: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
             mbar_init(smem_u32(&tempty_bar[s]), two ? 2 * kEpiWarps : kEpiWarps);
         }
-        for (int s = 0; s < kEpiWarps; ++s) mbar_init(smem_u32(&zin_bar[s]), 1);
+        for (int s = 0; s < kEpiWarps; ++s) {
+            mbar_init(smem_u32(&zin_bar[s][0]), 1);
+            mbar_init(smem_u32(&zin_bar[s][1]), 1);
+        }
         fence_mbar_init();
     }
     if (warp == kAllocWarp) {
@@ -798,7 +817,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
                 const uint32_t b_dst = a_dst + kABytes;
                 const int ba = g.a_batched ? bb : 0, bbt = g.b_batched ? bb : 0;
-                if (issuer) {
+                if (g.dbg_skip & 1) {
+                    if (issuer && do_a && (!TWO || leader)) mbar_arrive(bar);
+                } else if (issuer) {
                     if constexpr (TWO) {
                         // pair mode: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
                         const uint32_t lbar = leader ? bar : mapa_u32(bar, 0);
@@ -910,6 +931,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (issuer) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
+                            if (g.dbg_skip & 2) break;
                             if constexpr (TWO) umma_ss_2cta(d_tmem, ad + k * a_ks, bd + k * b_ks, idesc, k > 0 ? 1u : acc0);
                             else umma_ss(d_tmem, ad + k * a_ks, bd + k * b_ks, idesc, k > 0 ? 1u : acc0);
                         }
@@ -943,7 +965,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = warp;
         const int q = e & 3;    // TMEM lane quarter == warp id % 4
         const int half = e >> 2;  // which 32-column chunks of every kChunkStride this warp drains (0 .. kEpiWarps/4-1)
-        uint32_t as = 0, aphase = 0, zphase = 0;
+        uint32_t as = 0, aphase = 0;
+        const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * g.epi_warp_bytes;
+        // Stream of TMA-loaded epilogue inputs (saved pre-activation / residual chunks): the chunks this warp will drain
+        // are known in advance (tile t, t + stride, ...; columns half*32, + kChunkStride, ...), so a cursor runs
+        // g.zdepth chunks ahead of the consumer, across tile boundaries, and every slot is re-armed right after it has
+        // been read.  Measured (profiles/r1s3_gemm_experiments.txt): neither two chunks of lookahead (MC_GEMM_ZDEPTH=2, costs a
+        // ring stage) nor L2 promotion of these loads (MC_GEMM_ZPROMO) moves the GELU-backward epilogue (63 us on its own
+        // for the B/32 dZ2 GEMM against 44 us for the forward epilogue), so the default stays at one chunk.
+        constexpr bool kStream = EPI == EPI_ACT_BWD || EPI == EPI_RESID;
+        const bool stream = kStream && g.tma_epi;
+        int pf_t = work0, pf_c = half * 32, pf_n0 = 0, pf_m = 0, pf_b = 0;
+        auto pf_settle = [&]() {   // move the cursor to the next (tile, chunk) that exists for this warp
+            while (pf_t < g.num_tiles) {
+                const TileCoord pc = decode_tile(g, pf_t, cta_rank);
+                pf_n0 = pc.tn * g.BN; pf_m = pc.tm * BM + q * 32; pf_b = pc.b;
+                if (pf_c < g.BN && pf_n0 + pf_c < g.N) return;
+                pf_t += work_stride;
+                pf_c = half * 32;
+            }
+        };
+        uint32_t zslot = 0, zphase_bits = 0;
+        if (stream) {
+            pf_settle();
+            for (int d = 0; d < g.zdepth; ++d) {
+                if (pf_t < g.num_tiles) {
+                    if (lane == 0) {
+                        const uint32_t zb = smem_u32(&zin_bar[e][d]);
+                        mbar_arrive_expect_tx(zb, EPI == EPI_RESID ? 4096u : 2048u);
+                        tma_load_3d(stage_buf + (EPI == EPI_RESID ? 0u : 2048u + 2048u * d), &tmZ, zb, pf_n0 + pf_c, pf_m, pf_b);
+                    }
+                    pf_c += kChunkStride;
+                    pf_settle();
+                }
+            }
+        }
         float rs_acc[2] = {0.f, 0.f};   // fused row sums, one slot per m-tile this CTA can meet (tiles_m_eff <= 2)
         int rs_row[2] = {-1, -1};
         for (int t = work0; t < g.num_tiles; t += work_stride) {
@@ -955,30 +1011,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float bias_m = 0.f;
             if (g.bias_mode == MC_BIAS_M && row_ok) bias_m = g.bias[m];
             if (EPI == EPI_ACT_BWD_DUAL && g.bias2 != nullptr && row_ok) bias_m = g.bias2[m];
-            const uint32_t stage_buf = tiles_base + g.epi_smem_off + e * kEpiWarpBytes;
-            const uint32_t zbar = smem_u32(&zin_bar[e]);
-            if ((EPI == EPI_ACT_BWD || EPI == EPI_RESID) && g.tma_epi && lane == 0 && half * 32 < g.BN &&
-                n0 + half * 32 < g.N) {
-                // first pre-activation / residual chunk of this tile: in flight while the tile's MMAs finish
-                const uint32_t bytes = EPI == EPI_RESID ? 4096u : 2048u;
-                mbar_arrive_expect_tx(zbar, bytes);
-                tma_load_3d(stage_buf + (EPI == EPI_RESID ? 0u : 2048u), &tmZ, zbar, n0 + half * 32, tc.tm * BM + q * 32, tc.b);
-            }
             mbar_wait_relaxed(smem_u32(&tfull_bar[as]), aphase, 64);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
             float rsum = 0.f;
             for (int c = half * 32; c < g.BN; c += kChunkStride) {
                 const int nb = n0 + c;
-                if (nb >= g.N) break;  // warp-uniform
+                if (nb >= g.N || (g.dbg_skip & 4)) break;  // warp-uniform
                 const int rem = g.N - nb;
                 if (EPI == EPI_TRANS) {
                     chunk32_trans(g, t_row + c, bias_m, m, row_ok, tc.b, nb);
                 } else if (EPI != EPI_GENERIC && g.tma_epi) {
-                    const int next_n = (c + kChunkStride < g.BN && nb + kChunkStride < g.N) ? nb + kChunkStride : -1;
+                    const bool pf_ok = kStream && pf_t < g.num_tiles;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
-                                        nb, lane, zbar, zphase, next_n, rsum);
-                    if (EPI == EPI_ACT_BWD || EPI == EPI_RESID) zphase ^= 1u;
+                                        nb, lane, smem_u32(&zin_bar[e][zslot]), (zphase_bits >> zslot) & 1u,
+                                        EPI == EPI_RESID ? 0u : 2048u + 2048u * zslot, pf_ok ? pf_n0 + pf_c : -1, pf_m, pf_b, rsum);
+                    if (kStream) {
+                        zphase_bits ^= 1u << zslot;
+                        if (++zslot == (uint32_t)g.zdepth) zslot = 0;
+                        if (pf_ok) {
+                            pf_c += kChunkStride;
+                            pf_settle();
+                        }
+                    }
                 } else if (EPI != EPI_GENERIC && rem >= 32) {
                     chunk32<EPI>(g, t_row + c, bias_m, crow, tc.b, nb, row_ok, rsum);
                 } else {
@@ -1112,16 +1167,20 @@ int env_int(const char* name, int dflt) {
 
 // output tensor [batch][rows][cols] (cols contiguous) as a TMA store target with a [32 x 32] box
 int make_store_map(CUtensorMap* map, void* ptr, CUtensorMapDataType dt, int esz, int64_t cols, int64_t rows, int64_t batch,
-                   int64_t ld, int64_t batch_stride, const char* name) {
+                   int64_t ld, int64_t batch_stride, const char* name, int l2_promotion_bytes = 0) {
     EncodeTiledFn enc = get_encode_fn();
     MC_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     const bool batched = batch_stride != 0 && batch > 1;
     cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, batched ? (cuuint64_t)batch : 1};
     cuuint64_t gstride[2] = {(cuuint64_t)ld * esz, batched ? (cuuint64_t)batch_stride * esz : (cuuint64_t)ld * esz * rows};
     cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    // maps that are LOADED through (saved pre-activations: 64-byte row segments of lines whose other half another warp
+    // asks for a moment later) let L2 fetch whole 128 / 256-byte blocks from DRAM
+    const CUtensorMapL2promotion promo = l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                         : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                     : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     CUresult r = enc(map, dt, 3, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with %d", name, (int)r);
     return MC_OK;
 }
@@ -1243,6 +1302,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.b_box_rows = g.BN / g.cluster;
     static const int prod2 = env_int("MC_GEMM_PROD2", 1);
     g.prod2 = prod2 ? 1 : 0;
+    g.dbg_skip = env_int("MC_GEMM_DEBUG_SKIP", 0);
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
     const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;
     g.b_tx_bytes = g.b_mn ? (int)(ceil_div(bn_cta, 64) * kGroupBytes) : bn_cta * BK * 2;
@@ -1280,7 +1340,10 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.tma_epi = allow_tma_epi && epi != EPI_GENERIC && epi != EPI_TRANS && p->row_remap == 0 && al16(p->R, p->ldr, p->r_batch_stride, 4) &&
                 al16(p->C, p->ldc, p->c_batch_stride, c_bf16 ? 2 : 4) && al16(p->zout, p->ldz, p->z_batch_stride, 2) &&
                 al16(p->zin, p->ldzin, p->zin_batch_stride, 2);
-    const int epi_bytes = g.tma_epi ? kEpiWarps * (int)kEpiWarpBytes : 0;
+    static const int zdepth_env = env_int("MC_GEMM_ZDEPTH", 1);
+    g.zdepth = (epi == EPI_ACT_BWD && zdepth_env >= 2) ? 2 : 1;
+    g.epi_warp_bytes = (int)kEpiWarpBytes + (g.zdepth - 1) * 2048;
+    const int epi_bytes = g.tma_epi ? kEpiWarps * g.epi_warp_bytes : 0;
     const int smem_budget = 225 * 1024 - epi_bytes;
     g.stages = smem_budget / g.stage_bytes;
     if (g.stages > kMaxStages) g.stages = kMaxStages;
@@ -1327,8 +1390,9 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
         if (rc != MC_OK) return rc;
     }
     if (g.tma_epi && epi == EPI_RESID) {   // only the residual goes through TMA (loaded); C is stored directly
+        static const int rpromo = env_int("MC_GEMM_RPROMO", 0);
         rc = make_store_map(&tmZ, const_cast<float*>(p->R), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->N, p->M, g.out_batch, p->ldr,
-                            p->r_batch_stride, "R");
+                            p->r_batch_stride, "R", rpromo);
         if (rc != MC_OK) return rc;
     } else if (g.tma_epi) {
         const int esz = c_bf16 ? 2 : 4;
@@ -1340,8 +1404,9 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
                                 p->z_batch_stride, "Z");
             if (rc != MC_OK) return rc;
         } else if (epi == EPI_ACT_BWD) {   // the saved pre-activations are LOADED through the same box geometry
+            static const int zpromo = env_int("MC_GEMM_ZPROMO", 0);
             rc = make_store_map(&tmZ, const_cast<void*>(p->zin), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->N, p->M, g.out_batch,
-                                p->ldzin, p->zin_batch_stride, "Zin");
+                                p->ldzin, p->zin_batch_stride, "Zin", zpromo);
             if (rc != MC_OK) return rc;
         }
     }
