@@ -248,8 +248,8 @@ def main():
         traffic, traffic_src = None, None
         try:   # DRAM bytes of the same launch set (one step), from the committed ncu launch list of this workload
             from clip_mixer_b200.engine import fused_token_mix_enabled
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1s2_gemm_traffic.json" if fused_token_mix_enabled()
-                                             else "r1_final_gemm_traffic.json")))
+            names = ["r1s3_gemm_traffic.json", "r1s2_gemm_traffic.json"] if fused_token_mix_enabled() else ["r1_final_gemm_traffic.json"]
+            tj = json.load(open(next(f for f in (os.path.join(ROOT, "profiles", n) for n in names) if os.path.exists(f))))
             if args.model == "B32" and B == 256:
                 traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
         except Exception:
