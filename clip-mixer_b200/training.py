@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import checkpoint, ops
 from ._lib import MixerClipError
 from .dp import DataParallel
 from .optim import FusedAdamW, cosine_warmup_lr
@@ -374,24 +374,28 @@ class Trainer:
         need datasets that are not reachable offline.  The zero-shot scoring shape is in zeroshot.py."""
         return None
 
-    def save_model(self, currentEpoch: int, currentStep: int = 0):
+    def save_model(self, currentEpoch: int, currentStep: int = 0, savePath: Optional[str] = None):
+        """training.py:218-229: ``accelerator.save_state(path)`` + ``epoch.json`` + barrier (the Azure mirror is out of
+        scope).  The directory has accelerate's layout (checkpoint.py), so a run can be resumed by either side."""
+        path = savePath if savePath else "outputs/checkpoints"
+        checkpoint.save_state(path, self.model, self.optimizer, self.stepper.sched_step,
+                              total_steps=self.epochs * self.numBatches, rank=self.rank)
         if self.rank == 0:
-            os.makedirs("outputs/checkpoints", exist_ok=True)
-            torch.save({"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
-                        "sched_step": self.stepper.sched_step}, "outputs/checkpoints/state.pt")
-            with open("outputs/checkpoints/epoch.json", "w") as f:
-                json.dump({"epoch": currentEpoch, "step": currentStep}, f)          # training.py:223
+            checkpoint.write_epoch_json(path, currentEpoch, currentStep)                # training.py:223
         if dist.is_initialized():
             dist.barrier()
 
-    def load_model(self):
+    def load_model(self, path: str = "outputs/checkpoints"):
         try:
-            with open("outputs/checkpoints/epoch.json") as f:
-                meta = json.load(f)
-            st = torch.load("outputs/checkpoints/state.pt", map_location=self.model.logit_scale.device)
-            self.model.load_state_dict(st["model"])
-            self.optimizer.load_state_dict(st["optimizer"])
-            self.stepper.sched_step = st["sched_step"]
-            return meta["epoch"], meta["step"]
-        except Exception:                                                           # training.py:245-248
+            sched_step = checkpoint.load_state(path, self.model, self.optimizer)       # training.py:243
+            meta = checkpoint.read_epoch_json(path)                                     # training.py:244
+        except Exception as e:                                                          # training.py:245-248
+            if self.rank == 0 and os.path.isdir(path):
+                print(f"Could not load model, starting from scratch because {e}")
             return 0, 0
+        self.stepper.sched_step = sched_step
+        self.model.mark_weights_dirty()
+        store = self.model._require_store()
+        if store.flat_w16 is not None:
+            store.refresh_mirror(force=True)
+        return meta["epoch"], meta["step"]

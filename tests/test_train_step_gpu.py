@@ -120,3 +120,36 @@ def test_micro_batched_step_is_exact(precision, tol):
                                       abs(float(grads["logit_scale"]) - float(truth["grads"]["logit_scale"])) <= tol * cond)]
     print(f"[micro-batch/{precision}] worst grad err {worst:.2e}")
     assert not fails, fails[:5]
+
+
+def test_trainer_resumes_from_accelerate_layout_checkpoint(tmp_path, monkeypatch):
+    """training.py:106,218-250: a run that saves after 3 of 6 steps and is restarted continues exactly where the
+    uninterrupted run went (weights, AdamW moments and step, schedule position, data position)."""
+    from clip_mixer_b200.training import Trainer
+    from oracle import mixer_clip_oracle as O
+    monkeypatch.chdir(tmp_path)
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    full = Trainer(_model(cfg, sd, "fp32"), batch_size=8, steps_per_epoch=6)
+    assert (full.startEpoch, full.currentStep) == (0, 0)
+    ref = full.train()
+    assert len(ref) == 6
+
+    first = Trainer(_model(cfg, sd, "fp32"), batch_size=8, steps_per_epoch=6)
+    head = []
+    for idx, (images, texts) in enumerate(first.trainLoader):
+        if idx == 3:
+            break
+        head.append(float(first.stepper.step(images, texts)))
+    first.save_model(0, 3)
+    assert sorted(os.listdir("outputs/checkpoints")) == sorted(
+        ["epoch.json", "model.safetensors", "optimizer.bin", "random_states_0.pkl", "scheduler.bin"])
+
+    resumed = Trainer(_model(cfg, sd, "fp32"), batch_size=8, steps_per_epoch=6)
+    assert (resumed.startEpoch, resumed.currentStep) == (0, 3)
+    assert resumed.optimizer.t == 3 and resumed.stepper.sched_step == 3
+    tail = resumed.train()
+    got = head + tail
+    assert len(got) == 6
+    for a, b in zip(got, ref):
+        assert abs(a - b) <= 1e-4 * abs(b), (got, ref)
