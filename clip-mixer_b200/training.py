@@ -233,24 +233,27 @@ class FusedTrainStep:
             self.store.refresh_mirror(force=True)
         self.model._trusted_mirror = True     # do not bake a redundant cast pass into the graph
         candidates = self._split_candidates(images.shape[0])
-        graphs = []
-        for cand in candidates:
-            self.sm_split = cand
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._device_step(self.static_images, self.static_texts)
-            graphs.append(graph)
+        graphs = self._capture_candidates(candidates)
         pick = 0
         if len(candidates) > 1:
             # Interleaved timing (blocks of replays alternate over the candidates, so clock / power drift hits all of
             # them alike: back-to-back blocks of one candidate differ by more than the candidates do).  The replays are
             # real optimizer steps, so the state is put back afterwards.
-            total = [0.0] * len(candidates)
-            for _ in range(3):
-                for i, graph in enumerate(graphs):
-                    total[i] += self._time_graph(graph)
-            self.sm_split_trials = [(c, t / 3) for c, t in zip(candidates, total)]
-            pick = min(range(len(candidates)), key=lambda i: total[i])
+            times = self._time_interleaved(graphs)
+            pick = min(range(len(candidates)), key=lambda i: times[i])
+            self.sm_split_trials = list(zip(candidates, times))
+            if self.world > 1 and candidates[pick] is not None:
+                # Data parallel: NCCL's all-reduce kernels need SMs too, and a persistent kernel whose CTAs do not all
+                # fit at once runs in two waves.  Second round: the winning shares with 4 / 8 SMs left unassigned
+                # (NCCL keeps its own CTA count - capping it exposes the all-reduce tail, profiles/r1s3_gemm_experiments.txt).
+                a, b = candidates[pick]
+                extra = [(a - r // 2, b - r // 2) for r in (4, 8) if min(a, b) - r // 2 >= 8]
+                g2 = [graphs[pick]] + self._capture_candidates(extra)
+                t2 = self._time_interleaved(g2)
+                self.sm_split_trials += list(zip(extra, t2[1:]))
+                best2 = min(range(len(g2)), key=lambda i: t2[i])
+                if best2 > 0:
+                    candidates, graphs, pick = candidates + extra, graphs + g2[1:], len(candidates) + best2 - 1
             self.store.flat_p.copy_(snap_p)
             self.opt.m.copy_(snap_m)
             self.opt.v.copy_(snap_v)
@@ -258,6 +261,23 @@ class FusedTrainStep:
                 self.store.refresh_mirror(force=True)
             self.model._trusted_mirror = True
         self.sm_split, self.graph = candidates[pick], graphs[pick]
+
+    def _capture_candidates(self, candidates):
+        graphs = []
+        for cand in candidates:
+            self.sm_split = cand
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._device_step(self.static_images, self.static_texts)
+            graphs.append(graph)
+        return graphs
+
+    def _time_interleaved(self, graphs, rounds: int = 3):
+        total = [0.0] * len(graphs)
+        for _ in range(rounds):
+            for i, graph in enumerate(graphs):
+                total[i] += self._time_graph(graph)
+        return [t / rounds for t in total]
 
     def _split_candidates(self, n):
         """SM shares (image, text) to try at capture; [None] = no split."""
