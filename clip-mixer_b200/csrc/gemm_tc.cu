@@ -60,7 +60,11 @@ struct GemmTcArgs {
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
-    int dbg_skip;                           // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue
+    // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
+    // loads a stage's full barrier no longer depends on the second producer warp, so that warp can be lapped by two
+    // phases and the watchdog traps the launch (seen under ncu and with the residual epilogue): use with MC_GEMM_PROD2=0
+    // and treat a trap as "rerun", never as a product failure.
+    int dbg_skip;
     int epi_smem_off;                       // byte offset of the epilogue staging area from tiles_base
     // epilogue
     void* C;

@@ -26,6 +26,22 @@ from .dp import DataParallel
 from .optim import FusedAdamW, cosine_warmup_lr
 
 
+def parse_sm_split(value: str):
+    """MC_SM_SPLIT -> (fixed shares or None, tune at capture?): 'auto' | 'off' | 'image_sms,text_sms'."""
+    v = value.strip().lower()
+    if v == "auto":
+        return None, True
+    if v in ("", "off", "0", "none"):
+        return None, False
+    try:
+        shares = tuple(int(x) for x in v.split(","))
+    except ValueError:
+        shares = ()
+    if len(shares) != 2 or min(shares) < 2:
+        raise MixerClipError(f"MC_SM_SPLIT={value!r}: expected 'image_sms,text_sms', 'auto' or 'off'")
+    return shares, False
+
+
 class FusedTrainStep:
     """One optimisation step on a per-rank batch.  ``step(images, texts)`` returns the (device) loss of
     this rank; nothing is read back to the host."""
@@ -59,15 +75,7 @@ class FusedTrainStep:
         # instead of each taking turns on the whole GPU (every kernel of this step holds a full SM per CTA).
         # MC_SM_SPLIT = "image_sms,text_sms" fixes the shares, "off" sizes every kernel for all SMs, "auto" (default,
         # CUDA-graph mode only) times a few shares around the towers' FLOP ratio at capture and keeps the fastest.
-        split = os.environ.get("MC_SM_SPLIT", "auto").strip().lower()
-        self.sm_split = None
-        self.sm_split_auto = False
-        if split == "auto":
-            self.sm_split_auto = True
-        elif split not in ("", "off", "0", "none"):
-            self.sm_split = tuple(int(v) for v in split.split(","))
-            if len(self.sm_split) != 2 or min(self.sm_split) < 2:
-                raise MixerClipError(f"MC_SM_SPLIT={split!r}: expected 'image_sms,text_sms', 'auto' or 'off'")
+        self.sm_split, self.sm_split_auto = parse_sm_split(os.environ.get("MC_SM_SPLIT", "auto"))
         self.sm_split_trials = []
 
     def _tower_sms(self, which: int):

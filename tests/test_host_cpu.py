@@ -188,3 +188,33 @@ def test_data_parallel_gloo_world2(tmp_path):
     port = _free_port()
     mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_sm_split_setting_and_candidates(monkeypatch):
+    """MC_SM_SPLIT parsing and the candidate shares of the capture-time tuner (training.FusedTrainStep): 'auto' centres on
+    the towers' mixer-GEMM FLOP ratio, explicit shares are taken as they are, 'off' disables the split."""
+    import types
+    from clip_mixer_b200 import ops, training
+    from clip_mixer_b200._lib import MixerClipError
+
+    assert training.parse_sm_split("auto") == (None, True)
+    assert training.parse_sm_split(" OFF ") == (None, False) and training.parse_sm_split("") == (None, False)
+    assert training.parse_sm_split("84,64") == ((84, 64), False)
+    for bad in ("banana", "84", "84,64,2", "84,0"):
+        with pytest.raises(MixerClipError):
+            training.parse_sm_split(bad)
+
+    def stepper(setting, micro=None):
+        st = training.FusedTrainStep.__new__(training.FusedTrainStep)
+        st.overlap_towers, st.micro_batch, st.world = True, micro, 1
+        st.model = types.SimpleNamespace(_towers={"image": types.SimpleNamespace(P=50, D=768, L=12),
+                                                  "text": types.SimpleNamespace(P=77, D=512, L=12)})
+        st.sm_split, st.sm_split_auto = training.parse_sm_split(setting)
+        return st
+
+    monkeypatch.setattr(ops, "device_info", lambda: (148, 10, 0))
+    c = stepper("auto")._split_candidates(256)
+    assert c[0] is None and (86, 62) in c and (82, 66) in c and all(a + b == 148 and a % 2 == 0 for a, b in c[1:])
+    assert stepper("off")._split_candidates(256) == [None]
+    assert stepper("84,64")._split_candidates(256) == [(84, 64)]
+    assert stepper("auto", micro=64)._split_candidates(256) == [None]    # micro-batched path runs the towers in turn
