@@ -12,10 +12,10 @@
 //   warp 13   : second TMA producer (B operand) when prod2
 //   warp 15   : MMA issuer     (elected lane, tcgen05.mma kind::f16, 128 / 256 x BN x 16, fp32 accum in TMEM)
 //
-// These GEMMs are L2->SM bandwidth bound with a 128 x 256 tile (48 KB of operands per 64-deep k-block
-// against ~42 B/clk/SM of L2 bandwidth), so the kernel runs as 2-CTA clusters along M: the two CTAs
-// compute vertically adjacent tiles, each loads its own A tile and HALF of the shared B tile, and TMA
-// multicast delivers both halves to both CTAs (32 KB instead of 48 KB per CTA per k-block).
+// Operand delivery through the smem ring paces these GEMMs (~42 B/clk/SM measured through this pipeline; the memory
+// system itself lands 114-125 B/clk/SM from L2, tools/ubench/l2_ingest.cu), so the fewer operand bytes a CTA needs per
+// k-block the better: the kernel runs as CTA pairs (tcgen05 cta_group::2) computing a 256 x BN tile, each CTA stages its
+// own 128 A rows and HALF of the B tile (32 KB instead of 48 KB per CTA per k-block).
 //
 // Operand layouts are described, not materialised: a K-major operand is one TMA box of
 // [rows x 64] bf16 per stage; an MN-major operand (the "transposed" view: token-mixing reads the
@@ -1169,7 +1169,7 @@ double model_cost(int64_t M, int64_t N, int64_t out_batch, int64_t kb_total, int
     const int64_t rounds = ceil_div(work, sms / cluster);
     const double kb = double(kb_total) / split;
     const double bytes = (BM + double(BN) / cluster) * BK * 2;
-    const double t_l2 = bytes / 38.0, t_mma = 2.0 * BN;   // L2->SM delivery ~36-40 B/clk/SM (profiles/r1c sweep)
+    const double t_l2 = bytes / 38.0, t_mma = 2.0 * BN;   // operand delivery through the ring ~36-40 B/clk/SM (profiles/r1c sweep)
     const double epi = BN * (heavy_epi ? 14.0 : 6.0);
     double tile = kb * (t_mma > t_l2 ? t_mma : t_l2);
     if (epi > tile) tile = epi;  // epilogue of tile i overlaps the MMAs of tile i+1
