@@ -8,4 +8,4 @@ timeout 200 python bench.py > gpurun_out/bench_s3.json 2> gpurun_out/bench_s3.er
 timeout 100 python tools/profile_step.py --dump gpurun_out/gemm_table_s3.txt > gpurun_out/profile_step_s3.log 2>&1 &&
 timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off \
     --csv --log-file gpurun_out/launches_s3.csv python tools/profile_step.py > gpurun_out/ncu_launches_s3.log 2>&1
-tail -2 gpurun_out/profile_step_s3.log gpurun_out/ncu_launches_s3.log
+tail -n 2 gpurun_out/profile_step_s3.log gpurun_out/ncu_launches_s3.log

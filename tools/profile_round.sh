@@ -13,4 +13,4 @@ ncu --set full --clock-control none --import-source on -k regex:token_mix -c 12 
 python tools/gemm_bench.py lin3 dw3 dz2 --iters 1 > gpurun_out/gemm_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o gpurun_out/gemm_full \
     python tools/gemm_bench.py lin3 dw3 dz2 --iters 1 > gpurun_out/ncu_gemm.log 2>&1
-tail -2 gpurun_out/profile_step.log gpurun_out/ncu_tm.log gpurun_out/ncu_gemm.log
+tail -n 2 gpurun_out/profile_step.log gpurun_out/ncu_tm.log gpurun_out/ncu_gemm.log
