@@ -59,6 +59,7 @@ struct GemmTcArgs {
     int tma_epi;                            // outputs leave through smem staging + TMA store
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
+    int exp_flags;                          // MC_GEMM_EXP bits: experiments that are off until validated on a GPU (1: plain remote arrive)
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
     // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
     // loads a stage's full barrier no longer depends on the second producer warp, so that warp can be lapped by two
@@ -705,6 +706,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_r
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
 }
+// default-semantics arrive on a barrier of another CTA of the cluster (no cluster-scope release fence).  The
+// release.cluster form below costs ~1 k clocks (tools/ubench/l2_ingest cluster rows; MEMBAR.ALL.CTA + ERRBAR + CGAERRBAR
+// in SASS, 8-11 % of the non-leader epilogue warps' ncu samples).  The accumulator hand-back only has to order the
+// tcgen05.ld reads, which tcgen05.fence::before_thread_sync does.  Opt-in (MC_GEMM_EXP bit 1) until validated on a GPU.
+__device__ __forceinline__ void mbar_arrive_cluster_plain(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -1082,7 +1090,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (two && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+                if (two && !leader) {
+                    if (g.exp_flags & 1) mbar_arrive_cluster_plain(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+                    else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+                }
                 else mbar_arrive(smem_u32(&tempty_bar[as]));
             }
             as ^= 1u;
@@ -1319,6 +1330,8 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     static const int prod2 = env_int("MC_GEMM_PROD2", 1);
     g.prod2 = prod2 ? 1 : 0;
     g.dbg_skip = env_int("MC_GEMM_DEBUG_SKIP", 0);
+    static const int exp_flags = env_int("MC_GEMM_EXP", 0);
+    g.exp_flags = exp_flags;
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
     const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;
     g.b_tx_bytes = g.b_mn ? (int)(ceil_div(bn_cta, 64) * kGroupBytes) : bn_cta * BK * 2;
