@@ -59,7 +59,7 @@ struct GemmTcArgs {
     int tma_epi;                            // outputs leave through smem staging + TMA store
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
-    int exp_flags;                          // MC_GEMM_EXP bits: experiments that are off until validated on a GPU (1: plain remote arrive)
+    int exp_flags;                          // MC_GEMM_EXP bits: experiments that are off until validated on a GPU (1: plain remote arrive, 2: lean MMA issuer loop)
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
     // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
     // loads a stage's full barrier no longer depends on the second producer warp, so that warp can be lapped by two
@@ -759,7 +759,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t zin_bar[kEpiWarps][2];
     __shared__ uint32_t tmem_base_smem;
 
+    // -DMC_UNIFORM_WARP_IDX (experiment, not the product build until measured on a GPU): a role index the compiler can
+    // prove warp-uniform turns the role branches into uniform control flow, so the producer / issuer / epilogue loops
+    // keep their counters, barrier addresses and descriptors in uniform registers: R2UR moves in this kernel 744 -> 37,
+    // 5800 -> 4870 SASS instructions, and the issuer's k-loop becomes ~35 uniform-datapath instructions (cuobjdump).
+#ifdef MC_UNIFORM_WARP_IDX
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#else
     const int warp = threadIdx.x >> 5;
+#endif
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
     const int csize = g.cluster;
@@ -924,7 +932,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // one elected lane issues the four tcgen05.mma of a k-block back to back.  A single-lane `if (lane == 0)` body
         // costs ~137 clocks per MMA in R2UR / ELECT overhead (tools/ubench/mma_rate.cu) - more than the 128 clocks a
         // 128 x 256 x 16 MMA occupies the tensor pipe.
-        if (!two || leader) {
+        if ((!two || leader) && (g.exp_flags & 2) && !g.dual) {
+            // ---- lean issuer (MC_GEMM_EXP bit 2; opt-in until measured) ----
+            // tools/ubench/ring_handover runs this very pipeline at 515 clocks per k-block where the loop below needs
+            // ~690 with the loads switched off; its SASS builds the descriptors with a handful of uniform-datapath
+            // instructions, the loop below with a dozen R2UR moves of 64-bit templates kept in vector registers.  Here
+            // the descriptor is assembled from 32-bit pieces inside the loop: low word = start address >> 4 | LBO field,
+            // high word = SBO / version / swizzle constant.
+            uint32_t is_issuer;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_issuer));
+            const bool issuer = is_issuer != 0;
+            const uint32_t idesc = make_idesc_bf16(two ? 2 * BM : BM, g.BN, g.a_mn, g.b_mn);
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, 128B swizzle
+            const uint32_t a_lbo = (g.a_mn ? (kGroupBytes >> 4) : 1u) << 16, b_lbo = (g.b_mn ? (kGroupBytes >> 4) : 1u) << 16;
+            const uint32_t a_ks = g.a_mn ? 128u : 2u, b_ks = g.b_mn ? 128u : 2u;
+            const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t nstages = (uint32_t)g.stages, stage_bytes = (uint32_t)g.stage_bytes;
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0, a_addr = tiles_base;
+            for (int t = work0; t < g.num_tiles; t += work_stride) {
+                const TileCoord tc = decode_tile(g, t, cta_rank);
+                mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kAccStride;
+                uint32_t acc = 0u;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(full0 + 8u * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = (a_addr >> 4) | a_lbo, b_lo = ((a_addr + kABytes) >> 4) | b_lbo;
+                    if (issuer) {
+#pragma unroll
+                        for (uint32_t k = 0; k < BK / 16; ++k) {
+                            const uint64_t ad = (uint64_t(kDescHi) << 32) | (a_lo + k * a_ks);
+                            const uint64_t bd = (uint64_t(kDescHi) << 32) | (b_lo + k * b_ks);
+                            if constexpr (TWO) umma_ss_2cta(d_tmem, ad, bd, idesc, k > 0 ? 1u : acc);
+                            else umma_ss(d_tmem, ad, bd, idesc, k > 0 ? 1u : acc);
+                        }
+                        if constexpr (TWO) umma_commit_2cta_mc(empty0 + 8u * stage, mc_mask);
+                        else if (csize == 1) umma_commit(empty0 + 8u * stage);
+                        else umma_commit_mc(empty0 + 8u * stage, mc_mask);
+                    }
+                    acc = 1u;
+                    a_addr += stage_bytes;
+                    if (++stage == nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                        a_addr = tiles_base;
+                    }
+                }
+                if (issuer) {
+                    if constexpr (TWO) umma_commit_2cta_mc(smem_u32(&tfull_bar[as]), mc_mask);
+                    else umma_commit(smem_u32(&tfull_bar[as]));
+                }
+                as ^= 1u;
+                if (as == 0) aphase ^= 1u;
+            }
+        } else if (!two || leader) {
             uint32_t is_issuer;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_issuer));
             const bool issuer = is_issuer != 0;
