@@ -79,6 +79,7 @@ SIGNATURES = {
     "mc_l2norm_bwd": [_P, _P, _P, _P, _P, _I32, _I64, _I64, _P],
     "mc_head_fwd_bwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _P, _I64, _P],
     "mc_sumsq": [_P, _I64, _P, _P],
+    "mc_sched_step": [_P, _P, _I64, C.c_double, C.c_double, _I64, C.c_double, C.c_double, C.c_double, _P],
     "mc_adamw": [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _F, _F, _F, _F, _F, _F, _P],
 }
 SPECIAL_RESTYPE = {"mc_last_error": C.c_char_p, "mc_head_workspace_bytes": C.c_int64}

@@ -112,14 +112,30 @@ def save_state(path: str, model, optimizer, sched_step: int, total_steps: int = 
         torch.save(flat_to_torch_adamw(optimizer.store, _named_shapes(model), optimizer.m, optimizer.v, optimizer.t,
                                        optimizer.lr, optimizer.betas, optimizer.eps, optimizer.weight_decay),
                    os.path.join(path, OPT_BIN))
-        torch.save({"last_epoch": int(sched_step), "_step_count": int(sched_step) + 1, "first_cycle_steps": int(total_steps),
-                    "step_in_cycle": int(sched_step) % max(int(total_steps), 1), "warmup_steps": 2},
-                   os.path.join(path, SCHED_BIN))
-    states = {"torch_manual_seed": torch.get_rng_state()}
+        torch.save(scheduler_state_dict(sched_step, total_steps, optimizer.lr), os.path.join(path, SCHED_BIN))
+    # accelerate writes this file with torch.save (not pickle.dump) and these keys (checkpointing.save_accelerator_state)
+    import random as _random
+    import numpy as _np
+    states = {"step": int(sched_step), "random_state": _random.getstate(), "numpy_random_seed": _np.random.get_state(),
+              "torch_manual_seed": torch.get_rng_state()}
     if torch.cuda.is_available():
         states["torch_cuda_manual_seed"] = torch.cuda.get_rng_state_all()
-    with open(os.path.join(path, f"random_states_{rank}.pkl"), "wb") as f:
-        pickle.dump(states, f)
+    torch.save(states, os.path.join(path, f"random_states_{rank}.pkl"))
+
+
+def scheduler_state_dict(sched_step: int, total_steps: int, max_lr: float = 5e-4, warmup_steps: int = 2):
+    """Key set of ``CosineAnnealingWarmupRestarts.state_dict()`` (= the scheduler's __dict__ minus the optimizer) for the
+    configuration of training.py:83-89 (cycle_mult 1, gamma 1, min_lr = max_lr / 100) after ``sched_step`` steps.
+    The package is absent here (unpinned pip dependency), so the key set is restated from its published source."""
+    from .optim import cosine_warmup_lr
+    first = max(int(total_steps), warmup_steps + 1)
+    min_lr = max_lr / 100
+    lr = cosine_warmup_lr(int(sched_step), first, max_lr, min_lr, warmup_steps)
+    return {"first_cycle_steps": first, "cycle_mult": 1.0, "base_max_lr": max_lr, "max_lr": max_lr, "min_lr": min_lr,
+            "warmup_steps": warmup_steps, "gamma": 1.0, "cur_cycle_steps": first, "cycle": int(sched_step) // first,
+            "step_in_cycle": int(sched_step) % first, "base_lrs": [min_lr, min_lr], "last_epoch": int(sched_step),
+            "_step_count": int(sched_step) + 1, "verbose": False, "_get_lr_called_within_step": False,
+            "_last_lr": [lr, lr]}
 
 
 def load_state(path: str, model, optimizer) -> int:
@@ -136,6 +152,8 @@ def load_state(path: str, model, optimizer) -> int:
     model.load_state_dict(sd)
     osd = torch.load(os.path.join(path, OPT_BIN), map_location="cpu", weights_only=False)
     optimizer.t = torch_adamw_to_flat(osd, optimizer.store, _named_shapes(model), optimizer.m, optimizer.v)
+    if hasattr(optimizer, "sync_device_counters"):
+        optimizer.sync_device_counters(t=optimizer.t)          # the Adam step count also lives on the device
     sched = torch.load(os.path.join(path, SCHED_BIN), map_location="cpu", weights_only=False)
     return int(sched.get("last_epoch", 0))
 

@@ -19,7 +19,11 @@ void set_last_error(const char* fmt, ...) {
 // some SMs to concurrent work: in data-parallel runs the NCCL all-reduce of the gradient buckets needs a few CTAs
 // resident WHILE the backward GEMMs run, and a persistent grid that fills every SM (each CTA takes a whole SM's shared
 // memory) would push the collective into the gaps between kernels.
-static int g_sm_limit = -1;
+// Two separate values: the environment default is read once and survives; mc_set_sm_limit(n > 0) overrides it
+// (FusedTrainStep sizes each tower's kernels for its share of the SMs) and mc_set_sm_limit(0) RESTORES the environment
+// default instead of discarding it.
+static int g_env_limit = -1;
+static int g_sm_override = 0;
 
 int sm_count() {
     static int cached = 0;
@@ -31,12 +35,15 @@ int sm_count() {
         else
             return 148;  // B200
     }
-    if (g_sm_limit < 0) {
+    if (g_env_limit < 0) {
         const char* v = getenv("MC_SM_LIMIT");
-        g_sm_limit = v ? atoi(v) : 0;
+        g_env_limit = v ? atoi(v) : 0;
+        if (g_env_limit < 0) g_env_limit = 0;
     }
     int n = cached;
-    if (g_sm_limit > 0 && g_sm_limit < n) n = g_sm_limit;
+    int lim = g_sm_override > 0 ? g_sm_override : g_env_limit;
+    if (g_sm_override > 0 && g_env_limit > 0 && g_env_limit < lim) lim = g_env_limit;
+    if (lim > 0 && lim < n) n = lim;
     return n & ~1;   // CTA pairs: keep it even
 }
 
@@ -45,7 +52,7 @@ int sm_count() {
 extern "C" int mc_version(void) { return 100; }
 
 extern "C" int mc_set_sm_limit(int sms) {
-    mc::g_sm_limit = sms > 0 ? sms : 0;
+    mc::g_sm_override = sms > 0 ? sms : 0;
     return MC_OK;
 }
 

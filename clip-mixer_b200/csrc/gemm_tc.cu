@@ -59,7 +59,7 @@ struct GemmTcArgs {
     int tma_epi;                            // outputs leave through smem staging + TMA store
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
-    int exp_flags;                          // MC_GEMM_EXP bits: experiments that are off until validated on a GPU (1: plain remote arrive, 2: lean MMA issuer loop)
+    int exp_flags;                          // MC_GEMM_EXP bits (default 3 since round 2): 1 plain remote arrive, 2 lean MMA issuer loop
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
     // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
     // loads a stage's full barrier no longer depends on the second producer warp, so that warp can be lapped by two
@@ -709,7 +709,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_r
 // default-semantics arrive on a barrier of another CTA of the cluster (no cluster-scope release fence).  The
 // release.cluster form below costs ~1 k clocks (tools/ubench/l2_ingest cluster rows; MEMBAR.ALL.CTA + ERRBAR + CGAERRBAR
 // in SASS, 8-11 % of the non-leader epilogue warps' ncu samples).  The accumulator hand-back only has to order the
-// tcgen05.ld reads, which tcgen05.fence::before_thread_sync does.  Opt-in (MC_GEMM_EXP bit 1) until validated on a GPU.
+// tcgen05.ld reads, which tcgen05.fence::before_thread_sync does.  MC_GEMM_EXP bit 1 (default on: dZ2 875 -> 934 TFLOP/s).
 __device__ __forceinline__ void mbar_arrive_cluster_plain(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -759,11 +759,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t zin_bar[kEpiWarps][2];
     __shared__ uint32_t tmem_base_smem;
 
-    // -DMC_UNIFORM_WARP_IDX (experiment, not the product build until measured on a GPU): a role index the compiler can
-    // prove warp-uniform turns the role branches into uniform control flow, so the producer / issuer / epilogue loops
-    // keep their counters, barrier addresses and descriptors in uniform registers: R2UR moves in this kernel 744 -> 37,
-    // 5800 -> 4870 SASS instructions, and the issuer's k-loop becomes ~35 uniform-datapath instructions (cuobjdump).
-#ifdef MC_UNIFORM_WARP_IDX
+    // A role index the compiler can prove warp-uniform turns the role branches into uniform control flow, so the
+    // producer / issuer / epilogue loops keep their counters, barrier addresses and descriptors in uniform registers:
+    // R2UR moves in this kernel 744 -> 37, 5800 -> 4870 SASS instructions, the issuer's k-loop becomes ~35
+    // uniform-datapath instructions (cuobjdump).  Measured on B200 (profiles/r2_first_experiments.txt): lin4 957 -> 1039,
+    // dW3 1171 -> 1259 TFLOP/s, whole step 15.18 -> 14.70 ms.  -DMC_DIVERGENT_WARP_IDX restores the plain index for A/B.
+#ifndef MC_DIVERGENT_WARP_IDX
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 #else
     const int warp = threadIdx.x >> 5;
@@ -933,7 +934,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // costs ~137 clocks per MMA in R2UR / ELECT overhead (tools/ubench/mma_rate.cu) - more than the 128 clocks a
         // 128 x 256 x 16 MMA occupies the tensor pipe.
         if ((!two || leader) && (g.exp_flags & 2) && !g.dual) {
-            // ---- lean issuer (MC_GEMM_EXP bit 2; opt-in until measured) ----
+            // ---- lean issuer (MC_GEMM_EXP bit 2, default on) ----
             // tools/ubench/ring_handover runs this very pipeline at 515 clocks per k-block where the loop below needs
             // ~690 with the loads switched off; its SASS builds the descriptors with a handful of uniform-datapath
             // instructions, the loop below with a dozen R2UR moves of 64-bit templates kept in vector registers.  Here
@@ -1393,7 +1394,7 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     static const int prod2 = env_int("MC_GEMM_PROD2", 1);
     g.prod2 = prod2 ? 1 : 0;
     g.dbg_skip = env_int("MC_GEMM_DEBUG_SKIP", 0);
-    static const int exp_flags = env_int("MC_GEMM_EXP", 0);
+    static const int exp_flags = env_int("MC_GEMM_EXP", 3);   // both measured wins (profiles/r2_first_experiments.txt); 0 = round-1 paths
     g.exp_flags = exp_flags;
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)
     const int bn_cta = g.two_cta ? g.BN / 2 : g.BN;

@@ -8,8 +8,15 @@
 namespace mc {
 namespace {
 
+// Rank-consistent (deterministic) global norm: every block writes its partial sum into a fixed slot and the LAST block
+// to finish (ticket counter) adds the slots in index order, so all data-parallel replicas - which hold bit-identical
+// all-reduced gradients - compute bit-identical clip coefficients (torch's clip_grad_norm_ is deterministic too).
+__device__ float g_sumsq_partials[4096];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
     __shared__ float red[8];
+    __shared__ bool last;
     float s = 0.f;
     const long long n4 = n / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -25,8 +32,52 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
         s += __shfl_xor_sync(0xffu, s, 4);
         s += __shfl_xor_sync(0xffu, s, 2);
         s += __shfl_xor_sync(0xffu, s, 1);
-        if (threadIdx.x == 0) atomicAdd(out, s);
+        if (threadIdx.x == 0) {
+            g_sumsq_partials[blockIdx.x] = s;
+            __threadfence();
+            last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+        }
     }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // fixed-order tree over the slots (same order on every launch and every rank)
+    float t = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(&g_sumsq_partials[i]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        out[0] += tot;
+        g_sumsq_ticket = 0;
+    }
+}
+
+// Per-step scalars on the DEVICE (graph-capturable, no pinned host slot to race on): state = {Adam step count t,
+// scheduler step s}; writes hyper = {lr(s), 1 - beta1^(t+1), 1 - beta2^(t+1)} and advances both counters.  The
+// schedule is CosineAnnealingWarmupRestarts with cycle_mult = 1, gamma = 1 (training/training.py:83-89), restated
+// in optim.py::cosine_warmup_lr; fixed_lr >= 0 bypasses it.
+__global__ void sched_step_kernel(long long* __restrict__ state, float* __restrict__ hyper, long long first_cycle_steps,
+                                  double max_lr, double min_lr, long long warmup_steps, double beta1, double beta2,
+                                  double fixed_lr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long t = state[0] + 1, s = state[1];
+    double lr = fixed_lr;
+    if (fixed_lr < 0.0) {
+        const long long in_cycle = s % first_cycle_steps;
+        if (in_cycle < warmup_steps) lr = (max_lr - min_lr) * double(in_cycle) / double(warmup_steps) + min_lr;
+        else
+            lr = min_lr + (max_lr - min_lr) *
+                              (1.0 + cos(3.14159265358979323846 * double(in_cycle - warmup_steps) /
+                                         double(first_cycle_steps - warmup_steps))) / 2.0;
+    }
+    hyper[0] = (float)lr;
+    hyper[1] = (float)(1.0 - pow(beta1, (double)t));
+    hyper[2] = (float)(1.0 - pow(beta2, (double)t));
+    state[0] = t;
+    state[1] = s + 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -78,9 +129,21 @@ extern "C" int mc_sumsq(const float* g, int64_t n, float* out, void* stream_) {
     if (n == 0) return MC_OK;
     MC_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
     int64_t blocks = ceil_div(n / 4 + 1, 256);
-    const int64_t cap = (int64_t)sm_count() * 8;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (cap > 4096) cap = 4096;
     if (blocks > cap) blocks = cap;
     sumsq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, n, out);
+    MC_CUDA(cudaGetLastError());
+    return MC_OK;
+}
+
+extern "C" int mc_sched_step(int64_t* state, float* hyper, int64_t first_cycle_steps, double max_lr, double min_lr,
+                             int64_t warmup_steps, double beta1, double beta2, double fixed_lr, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MC_CHECK(state != nullptr && hyper != nullptr, "sched_step: null state / hyper");
+    MC_CHECK(fixed_lr >= 0.0 || first_cycle_steps > warmup_steps, "sched_step: first_cycle_steps must exceed warmup_steps");
+    sched_step_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<long long*>(state), hyper, first_cycle_steps, max_lr, min_lr,
+                                            warmup_steps, beta1, beta2, fixed_lr);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }

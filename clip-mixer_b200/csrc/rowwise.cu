@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long x_row_stride,
               const int* __restrict__ row_index, const float* __restrict__ cls, long long cls_period,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-              const float* __restrict__ dres, float* __restrict__ dx, long long dx_row_stride,
+              const float* dres, float* dx, long long dx_row_stride,   // dres may alias dx (in-place residual add): no __restrict__
               void* __restrict__ dx_act, int act_dtype, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ colsum_out, float* __restrict__ rowsum_out, long long rowsum_period,
               float* __restrict__ dcls, long long rows, int D) {
@@ -188,8 +188,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
-                   float* __restrict__ dx, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres,
+                   float* dx /* dres may alias dx: every element is read, then written, by the same thread */, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
                    long long rowsum_period, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ colsum_out, long long rows, int D) {
     // Persistent over rows.  The column accumulators (dgamma, dbeta, column sums of dx) live in shared memory,

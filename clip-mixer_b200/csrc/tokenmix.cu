@@ -234,7 +234,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __shared__ __align__(8) uint64_t y_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
-#ifdef MC_UNIFORM_WARP_IDX
+#ifndef MC_DIVERGENT_WARP_IDX
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index (see gemm_tc.cu)
 #else
     const int warp = threadIdx.x >> 5;

@@ -16,7 +16,7 @@ from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_
                    GemmParams, MixerClipError, TokenMixParams, check)
 
 __all__ = ["gemm", "set_sm_limit", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
-           "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "adamw", "device_info",
+           "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "sched_step", "adamw", "device_info",
            "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
            "ACT_GELU_BWD", "launch_count", "reset_launch_count", "enable_gemm_timing", "collect_gemm_timing"]
 
@@ -290,6 +290,16 @@ def head_fwd_bwd(ui, ut, ui_all, ut_all, log_scale, n, N, E, rank, grad_scale, l
 
 def sumsq(g, n, out):
     check(_lib.load().mc_sumsq(_ptr(g), n, _ptr(out), _stream()), "mc_sumsq")
+    _count()
+
+
+def sched_step(state, hyper, first_cycle_steps, max_lr, min_lr, warmup_steps, beta1, beta2, fixed_lr=-1.0):
+    """Device-side scheduler + Adam step count: hyper = {lr, 1-b1^t, 1-b2^t}, state (int64 {t, s}) advanced."""
+    if state.dtype != torch.int64 or hyper.dtype != torch.float32:
+        raise MixerClipError("sched_step: state must be int64[2] and hyper fp32[3]")
+    check(_lib.load().mc_sched_step(_ptr(state), _ptr(hyper), int(first_cycle_steps), float(max_lr), float(min_lr),
+                                    int(warmup_steps), float(beta1), float(beta2), float(fixed_lr), _stream()),
+          "mc_sched_step")
     _count()
 
 

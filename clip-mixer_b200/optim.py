@@ -52,20 +52,40 @@ class FusedAdamW:
         self.m = torch.zeros(store.total, device=dev)
         self.v = torch.zeros(store.total, device=dev)
         self.sumsq = torch.zeros(1, device=dev)
+        # Per-step scalars {lr, 1-b1^t, 1-b2^t} live on the DEVICE and are produced by mc_sched_step from the device
+        # counters `state` = {Adam step count t, scheduler step s}, inside the (graph-capturable) step.  Round 1 staged
+        # them through ONE pinned host slot per step: with no host sync in the loop the host ran ahead of the GPU and
+        # step k+1 could overwrite the slot before step k's async copy had read it.
         self.hyper = torch.zeros(3, device=dev)
-        self.hyper_host = torch.zeros(3, pin_memory=True)
-        self.t = 0
+        self.state = torch.zeros(2, device=dev, dtype=torch.int64)
+        self.t = 0                         # host mirror of state[0] (checkpoints)
+        self.schedule = None               # (first_cycle_steps, max_lr, min_lr, warmup_steps) or None = fixed self.lr
 
-    def set_step_scalars(self, lr: float):
-        """Host side of a step: advance t and stage {lr, 1-b1^t, 1-b2^t} (pinned -> device, async)."""
-        self.t += 1
-        self.hyper_host[0] = lr
-        self.hyper_host[1] = 1.0 - self.betas[0] ** self.t
-        self.hyper_host[2] = 1.0 - self.betas[1] ** self.t
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+    def set_schedule(self, first_cycle_steps: int, max_lr: float, min_lr: float, warmup_steps: int):
+        """Cosine-with-warm-up learning rate computed on the device from the scheduler step (training.py:83-89)."""
+        if first_cycle_steps <= warmup_steps:
+            raise ValueError("first_cycle_steps must exceed warmup_steps")
+        self.schedule = (int(first_cycle_steps), float(max_lr), float(min_lr), int(warmup_steps))
+
+    def sync_device_counters(self, t: int = None, sched_step: int = None):
+        """Write the host view of {t, s} to the device (after load_state_dict / capture-time tuning replays)."""
+        if t is not None:
+            self.t = int(t)
+        cur = self.state.tolist()
+        self.state.copy_(torch.tensor([self.t, cur[1] if sched_step is None else int(sched_step)], dtype=torch.int64))
+
+    def launch_scalars(self, fixed_lr: float = None):
+        """Device side, graph-capturable: advance {t, s} and write hyper for this step."""
+        if fixed_lr is None and self.schedule is not None:
+            f, mx, mn, w = self.schedule
+            ops.sched_step(self.state, self.hyper, f, mx, mn, w, self.betas[0], self.betas[1], -1.0)
+        else:
+            ops.sched_step(self.state, self.hyper, 1, 0.0, 0.0, 0, self.betas[0], self.betas[1],
+                           self.lr if fixed_lr is None else fixed_lr)
 
     def launch(self, grad_mul: float = 1.0):
-        """Device side (graph-capturable): grad norm + AdamW + bf16 mirror refresh."""
+        """Device side (graph-capturable): grad norm + AdamW + bf16 mirror refresh.  hyper must have been written for
+        this step by launch_scalars()."""
         st = self.store
         if st.flat_g is None:
             raise MixerClipError("FusedAdamW.step before any backward")
@@ -82,7 +102,8 @@ class FusedAdamW:
             st.mirror_is_current()
 
     def step(self, lr: float = None, grad_mul: float = 1.0):
-        self.set_step_scalars(self.lr if lr is None else lr)
+        self.launch_scalars(self.lr if lr is None else lr)
+        self.t += 1
         self.launch(grad_mul)
 
     def grad_norm(self) -> torch.Tensor:
@@ -99,4 +120,4 @@ class FusedAdamW:
     def load_state_dict(self, sd):
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
-        self.t = int(sd["t"])
+        self.sync_device_counters(t=int(sd["t"]))

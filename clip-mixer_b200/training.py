@@ -59,7 +59,8 @@ class FusedTrainStep:
         self.store = store
         self.opt = optimizer if optimizer is not None else FusedAdamW(model, lr=max_lr)
         self.total_steps, self.max_lr, self.min_lr, self.warmup = total_steps, max_lr, max_lr / 100, warmup_steps
-        self.sched_step = 0
+        self._sched_step = 0
+        self.opt.set_schedule(total_steps, max_lr, max_lr / 100, warmup_steps)
         dev = store.device
         self.loss = torch.zeros(1, device=dev)
         self.use_graph = use_cuda_graph
@@ -90,6 +91,16 @@ class FusedTrainStep:
         return self._side
 
     # ---- schedule -----------------------------------------------------------------------------------
+    @property
+    def sched_step(self):
+        return self._sched_step
+
+    @sched_step.setter
+    def sched_step(self, value):
+        """Host view of the scheduler step; assigning it (checkpoint resume) also positions the device counter."""
+        self._sched_step = int(value)
+        self.opt.sync_device_counters(sched_step=self._sched_step)
+
     def current_lr(self):
         return cosine_warmup_lr(self.sched_step, self.total_steps, self.max_lr, self.min_lr, self.warmup)
 
@@ -157,6 +168,7 @@ class FusedTrainStep:
                 model.logit_scale.data.clamp_(0, math.log(100))
             else:
                 model.logit_scale.data.clamp_(max=100)
+        self.opt.launch_scalars()                                                   # lr(s), bias corrections: on the device
         self.opt.launch(grad_mul=1.0)                                               # clip + step            :181,185
 
     def _micro_batched_backward(self, images, texts):
@@ -208,7 +220,6 @@ class FusedTrainStep:
     def step(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
         if not (images.is_cuda and texts.is_cuda):
             raise MixerClipError("FusedTrainStep needs CUDA inputs (no CPU fallback)")
-        self.opt.set_step_scalars(self.current_lr())
         if not self.use_graph:
             self._device_step(images, texts)
         else:
@@ -218,7 +229,8 @@ class FusedTrainStep:
             self.static_texts.copy_(texts, non_blocking=True)
             self.graph.replay()
         self.model._trusted_mirror = True     # the optimizer kernel keeps the bf16 mirror current
-        self.sched_step += 1                                                        # scheduler.step()       :186
+        self.opt.t += 1                       # host mirrors of the device counters (advanced by mc_sched_step in the step)
+        self._sched_step += 1                                                       # scheduler.step()       :186
         return self.loss
 
     def _capture(self, images, texts):
@@ -237,6 +249,7 @@ class FusedTrainStep:
         self.store.flat_p.copy_(snap_p)
         self.opt.m.copy_(snap_m)
         self.opt.v.copy_(snap_v)
+        self.opt.sync_device_counters(sched_step=self._sched_step)   # the warm-up steps advanced the device counters
         if self.model._precision.act == torch.bfloat16:
             self.store.refresh_mirror(force=True)
         self.model._trusted_mirror = True     # do not bake a redundant cast pass into the graph
@@ -265,6 +278,7 @@ class FusedTrainStep:
             self.store.flat_p.copy_(snap_p)
             self.opt.m.copy_(snap_m)
             self.opt.v.copy_(snap_v)
+            self.opt.sync_device_counters(sched_step=self._sched_step)
             if self.model._precision.act == torch.bfloat16:
                 self.store.refresh_mirror(force=True)
             self.model._trusted_mirror = True
@@ -404,7 +418,9 @@ class Trainer:
 
     def save_model(self, currentEpoch: int, currentStep: int = 0, savePath: Optional[str] = None):
         """training.py:218-229: ``accelerator.save_state(path)`` + ``epoch.json`` + barrier (the Azure mirror is out of
-        scope).  The directory has accelerate's layout (checkpoint.py), so a run can be resumed by either side."""
+        scope).  The directory has accelerate's file layout (checkpoint.py): ``optimizer.bin`` loads into the reference's
+        torch.optim.AdamW and the model file into the reference's CLIP (both pinned by tests); the scheduler and RNG files
+        carry the key sets accelerate / CosineAnnealingWarmupRestarts write, restated without the packages (unpinned)."""
         path = savePath if savePath else "outputs/checkpoints"
         checkpoint.save_state(path, self.model, self.optimizer, self.stepper.sched_step,
                               total_steps=self.epochs * self.numBatches, rank=self.rank)

@@ -175,7 +175,9 @@ int mc_ln_fwd(const float* x, int64_t x_row_stride, const int32_t* row_index, co
  *   rowsum_out[r%P] += sum_d dx[r,d]                      (bias grad of token-mix lin2, may be NULL)
  * x rows are addressed like mc_ln_fwd (row_index / x_row_stride); dx rows likewise
  * (dx_row_stride); dy is dense [rows, D] fp32.  Rows with r % cls_period == 0 (cls != NULL) take
- * x from `cls` and accumulate their dx into dcls[D] instead of writing dx. */
+ * x from `cls` and accumulate their dx into dcls[D] instead of writing dx.
+ * Aliasing contract: dres MAY be the same buffer as dx (in-place residual-gradient add; each element is read and
+ * then written by one thread).  No other pair of arguments may overlap. */
 int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, const int32_t* row_index, const float* cls,
               int64_t cls_period, const float* mean, const float* rstd, const float* gamma, const float* dres,
               float* dx, int64_t dx_row_stride, void* dx_act, int32_t act_dtype, float* dgamma, float* dbeta,
@@ -237,8 +239,17 @@ int mc_head_fwd_bwd(const float* ui, const float* ut, const float* ui_all, const
  *             optional bf16 mirror of the new weights.  The per-step scalars come from DEVICE
  *             memory so a captured CUDA graph can be replayed while the schedule advances:
  *             hyper = {lr, 1 - beta1^t, 1 - beta2^t}.  sumsq may be NULL (no clipping).
+ *   mc_sched_step: the scheduler / step-count side of the same lines, ON THE DEVICE (so that a captured graph
+ *             replays with no host-written scalar that a later step could overwrite): state = int64 {t, s}
+ *             (Adam step count, scheduler step; training.py:185-186); writes hyper = {lr(s), 1 - beta1^(t+1),
+ *             1 - beta2^(t+1)} and stores {t+1, s+1}.  lr(s) = CosineAnnealingWarmupRestarts(first_cycle_steps,
+ *             max_lr, min_lr, warmup_steps, cycle_mult 1, gamma 1) of training.py:83-89, or fixed_lr when >= 0.
+ *   mc_sumsq is deterministic (per-block partials reduced in fixed order by the last block), so data-parallel
+ *             replicas holding identical all-reduced gradients clip with bit-identical coefficients.
  * ------------------------------------------------------------------------------------------ */
 int mc_sumsq(const float* g, int64_t n, float* out, void* stream);
+int mc_sched_step(int64_t* state, float* hyper, int64_t first_cycle_steps, double max_lr, double min_lr,
+                  int64_t warmup_steps, double beta1, double beta2, double fixed_lr, void* stream);
 int mc_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const uint8_t* decay_flags, int64_t n,
              const float* sumsq, const float* hyper, float grad_mul, float max_norm, float beta1, float beta2,
              float eps, float weight_decay, void* stream);

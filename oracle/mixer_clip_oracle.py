@@ -277,6 +277,38 @@ def loss_and_grads(sd, image, text, world: int = 1):
                 loss=total.detach(), logits_per_image=li, logits_per_text=lt, grads=grads)
 
 
+def loss_and_grads_chunked(sd, image, text, chunk: int, world: int = 1):
+    """Same result as loss_and_grads, computed micro-batch by micro-batch so that full-size batches (BASELINE
+    configs[1]: 256 samples) fit in host memory.  Exact, not an approximation: the gathered features are DETACHED
+    (training.py:158-159), so the loss of row i depends on row i's feature-with-grad and on all features without
+    grad.  Pass 1 computes all features without autograd, pass 2 back-propagates each chunk's rows
+    against them with labels offset like training.py:165-167."""
+    N = image.shape[0]
+    assert N % world == 0 and (N // world) % chunk == 0
+    n = N // world
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.no_grad():
+        feats = [clip_forward(params, image[i:i + chunk], text[i:i + chunk]) for i in range(0, N, chunk)]
+        ui_all = torch.cat([f[0] for f in feats])
+        ut_all = torch.cat([f[1] for f in feats])
+    total = 0.0
+    for r in range(world):
+        for k in range(n // chunk):
+            lo = r * n + k * chunk
+            ui, ut, s = clip_forward(params, image[lo:lo + chunk], text[lo:lo + chunk])
+            # labels of these rows inside rank r's block: arange(chunk) + r*n + k*chunk = "rank" (r*n/chunk + k)
+            loss_k, _, _ = contrastive_loss(ui, ut, s, ui_all, ut_all, rank=lo // chunk)
+            part = loss_k * (chunk / n) / world
+            part.backward()
+            total = total + float(part.detach())
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    with torch.no_grad():
+        s = params["logit_scale"].exp()
+        _, li, lt = contrastive_loss(ui_all[:n], ut_all[:n], s, ui_all, ut_all, rank=0)
+    return dict(image_features=ui_all, text_features=ut_all, logit_scale=s.detach(),
+                loss=torch.tensor(total, dtype=ui_all.dtype), logits_per_image=li, logits_per_text=lt, grads=grads)
+
+
 # --------------------------------------------------------------------------------------
 # closed-form head (what the fused CUDA head kernel computes; SURVEY 8-a8)
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,139 @@
+"""Parity of the BENCHMARKED configuration: BASELINE.json configs[1] - Mixer-CLIP B/32-size, 256
+samples, bf16 tensor-core engine - through exactly what bench.py times: FusedTrainStep with the step captured in a
+CUDA graph, the two towers on two streams with the SM split, any-factor split-K wgrads, uint8 images normalised inside
+the patch-embedding operand producer.  Loss and EVERY gradient are compared with the fp32 oracle run on the host on the
+same batch (micro-batched oracle, exact because the gathered features are detached; pinned in test_oracle_cpu.py).
+Tolerance: north_star's bf16 bound, 2e-2 per-tensor L2-relative.  Also: the contrastive head at BASELINE configs[2]
+scale (n = 4096 local rows against N = 32768 gathered rows, rank != 0) against the fp64 closed form."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+MEAN = (0.48145466, 0.4578275, 0.40821073)     # training.py:115 (Normalize after /255, :149)
+STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _b32(precision="bf16"):
+    from clip_mixer_b200.clip import CLIP
+    from oracle import mixer_clip_oracle as O
+    cfg = O.CONFIGS["B32"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    m = CLIP(cfg["embed_dim"], cfg["image_resolution"], cfg["vision_layers"], cfg["vision_width"],
+             cfg["vision_patch_size"], cfg["context_length"], cfg["vocab_size"], cfg["transformer_width"], 8,
+             cfg["transformer_layers"], useTransformer=False, precision=precision)
+    m.load_state_dict(sd)
+    return cfg, sd, m.to(DEV).train()
+
+
+def _model(cfg, sd, precision):
+    from clip_mixer_b200.clip import CLIP
+    m = CLIP(cfg["embed_dim"], cfg["image_resolution"], cfg["vision_layers"], cfg["vision_width"],
+             cfg["vision_patch_size"], cfg["context_length"], cfg["vocab_size"], cfg["transformer_width"],
+             max(1, cfg["transformer_width"] // 64), cfg["transformer_layers"], useTransformer=False, precision=precision)
+    m.load_state_dict(sd)
+    return m.to(DEV).train()
+
+
+def test_benchmarked_graph_step_b32_batch256_vs_oracle():
+    from clip_mixer_b200.training import FusedTrainStep, synthetic_batch
+    from oracle import mixer_clip_oracle as O
+    B = 256
+    cfg, sd, model = _b32()
+    images_u8, texts = synthetic_batch(model._cfg, B, 1000, DEV)           # bench.py's inputs (uint8 images)
+    assert images_u8.dtype == torch.uint8
+    stepper = FusedTrainStep(model, total_steps=10 ** 6, use_cuda_graph=True)
+    loss = stepper.step(images_u8, texts)                                   # capture (+ SM-split tuning) + ONE replay
+    torch.cuda.synchronize()
+    assert stepper.graph is not None
+    grads = {k: p.grad.detach().float().cpu().clone() for k, p in model.named_parameters()}
+    loss = float(loss)
+    # oracle on the host: the loop's /255 + Normalize (training.py:115,149), then the chunked exact step
+    img = images_u8.cpu().float() / 255.0
+    img = (img - torch.tensor(MEAN).view(1, 3, 1, 1)) / torch.tensor(STD).view(1, 3, 1, 1)
+    torch.set_num_threads(os.cpu_count())
+    truth = O.loss_and_grads_chunked(sd, img, texts.cpu(), chunk=32)
+    tol = 2e-2
+    e_loss = abs(loss - float(truth["loss"])) / abs(float(truth["loss"]))
+    worst, fails = O.compare_grads(grads, truth["grads"], tol)
+    errs = sorted(((O.l2_rel(grads[k], v), k) for k, v in truth["grads"].items()
+                   if float(v.norm()) > 1e-6 * math.sqrt(sum(float(t.norm()) ** 2 for t in truth["grads"].values()))),
+                  reverse=True)
+    ls_raw = abs(float(grads["logit_scale"]) - float(truth["grads"]["logit_scale"])) / abs(float(truth["grads"]["logit_scale"]))
+    print(f"[bench-path B32 b256 bf16 graph] sm_split={stepper.sm_split} loss {loss:.6f} vs {float(truth['loss']):.6f} "
+          f"(rel {e_loss:.2e}); worst gradient {worst:.2e}; median {errs[len(errs) // 2][0]:.2e}; "
+          f"logit_scale grad raw rel {ls_raw:.2e}; top: {[(k, round(e, 4)) for e, k in errs[:4]]}")
+    assert e_loss <= tol
+    assert not fails, sorted(fails, key=lambda t: -t[1])[:8]
+
+
+def test_graph_replay_without_host_sync_keeps_the_schedule():
+    """the per-step scalars {lr, 1-b1^t, 1-b2^t} used to travel through one pinned host slot that a
+    later step could overwrite before the copy ran.  They are now produced on the device inside the captured step; N
+    replays enqueued with NO host synchronisation must land on the same weights as N synchronised eager steps, and the
+    device counters / learning rate must be the schedule's."""
+    from clip_mixer_b200.optim import cosine_warmup_lr
+    from clip_mixer_b200.training import FusedTrainStep
+    from oracle import mixer_clip_oracle as O
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    steps = 12
+    image, text = O.synthetic_batch(cfg, 8, seed=1)
+    image, text = image.to(DEV), text.to(DEV)
+    finals = []
+    for use_graph in (False, True):
+        model = _model(cfg, sd, "fp32")
+        st = FusedTrainStep(model, total_steps=40, warmup_steps=2, use_cuda_graph=use_graph)
+        if use_graph:
+            st.step(image, text)                       # capture happens here (synchronises); the rest runs unsynchronised
+            torch.cuda._sleep(int(5e8))                # keep the GPU busy so the host really runs ahead of it
+            for _ in range(steps - 1):
+                st.step(image, text)
+        else:
+            for _ in range(steps):
+                st.step(image, text)
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        assert st.opt.state.tolist() == [steps, steps] and st.opt.t == steps and st.sched_step == steps
+        lr_last = cosine_warmup_lr(steps - 1, 40, 5e-4, 5e-6, 2)
+        hy = st.opt.hyper.tolist()
+        assert abs(hy[0] - lr_last) <= 1e-6 * lr_last
+        assert abs(hy[1] - (1 - 0.9 ** steps)) <= 1e-6 and abs(hy[2] - (1 - 0.98 ** steps)) <= 1e-6
+        finals.append({k: p.detach().double().cpu().clone() for k, p in model.named_parameters()})
+    worst = 0.0
+    for k in finals[0]:
+        upd0, upd1 = finals[0][k] - sd[k].double(), finals[1][k] - sd[k].double()
+        den = float(upd0.norm())
+        if den > 1e-12:
+            worst = max(worst, float((upd1 - upd0).norm()) / den)
+    print(f"[no-sync graph vs synced eager, {steps} steps] worst update difference {worst:.2e}")
+    assert worst <= 5e-3, worst
+
+
+@pytest.mark.parametrize("n,N,rank", [(4096, 32768, 5), (2048, 4096, 1)])
+def test_head_at_global_batch_scale_vs_closed_form(n, N, rank):
+    """BASELINE configs[2]: 8 ranks x 4096 rows against the 32768 gathered rows (training.py:55-56,158-168)."""
+    from clip_mixer_b200 import ops
+    from oracle import mixer_clip_oracle as O
+    E = 512
+    g = torch.Generator().manual_seed(8)
+    ui_all = torch.nn.functional.normalize(torch.randn(N, E, generator=g, dtype=torch.float64), dim=1)
+    ut_all = torch.nn.functional.normalize(torch.randn(N, E, generator=g, dtype=torch.float64) + 0.5 * ui_all, dim=1)
+    ui, ut = ui_all[rank * n:(rank + 1) * n], ut_all[rank * n:(rank + 1) * n]
+    t = torch.tensor(math.log(1 / 0.07), dtype=torch.float64)
+    torch.set_num_threads(os.cpu_count())
+    loss_ref, dui_ref, dut_ref, dt_ref = O.head_closed_form(ui, ut, t, ui_all, ut_all, rank)
+    c = lambda v: v.float().to(DEV).contiguous()
+    loss, dls = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dui, dut = torch.empty(n, E, device=DEV), torch.empty(n, E, device=DEV)
+    ws = torch.empty(ops.head_workspace_bytes(n, N, E) // 4, device=DEV)
+    ops.head_fwd_bwd(c(ui), c(ut), c(ui_all), c(ut_all), c(t.reshape(1)), n, N, E, rank, 1.0, loss, dui, dut, dls, ws)
+    torch.cuda.synchronize()
+    e = (abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()), O.l2_rel(dui, dui_ref), O.l2_rel(dut, dut_ref),
+         abs(dls.item() - dt_ref.item()) / max(1.0, abs(dt_ref.item())))
+    print(f"[head n={n} N={N} rank={rank}] loss {e[0]:.2e} dui {e[1]:.2e} dut {e[2]:.2e} dlogscale {e[3]:.2e}")
+    assert e[0] < 1e-5 and e[1] < 2e-5 and e[2] < 2e-5 and e[3] < 2e-5

@@ -97,6 +97,20 @@ def test_directory_round_trip(tmp_path):
         assert torch.equal(a, b), k
     assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v)
     assert checkpoint.read_epoch_json(path) == {"epoch": 2, "step": 5}
+    # scheduler.bin: full key set of CosineAnnealingWarmupRestarts.state_dict(); values follow cosine_warmup_lr
+    from clip_mixer_b200.optim import cosine_warmup_lr
+    sched = torch.load(os.path.join(path, "scheduler.bin"), weights_only=False)
+    assert {"first_cycle_steps", "cycle_mult", "base_max_lr", "max_lr", "min_lr", "warmup_steps", "gamma", "cur_cycle_steps",
+            "cycle", "step_in_cycle", "base_lrs", "last_epoch", "_step_count", "_last_lr"} <= set(sched)
+    assert sched["last_epoch"] == 11 and sched["step_in_cycle"] == 11 and sched["cycle"] == 0
+    assert abs(sched["_last_lr"][0] - cosine_warmup_lr(11, 100, 5e-4, 5e-6, 2)) < 1e-12
+    # random_states_<rank>.pkl: written with torch.save, accelerate's keys, and the torch RNG state round-trips
+    rng = torch.load(os.path.join(path, "random_states_0.pkl"), weights_only=False)
+    assert {"step", "random_state", "numpy_random_seed", "torch_manual_seed"} <= set(rng)
+    torch.set_rng_state(rng["torch_manual_seed"])
+    a = torch.rand(3)
+    torch.set_rng_state(rng["torch_manual_seed"])
+    assert torch.equal(a, torch.rand(3))
 
 
 def test_ddp_prefixed_weights_and_missing_directory(tmp_path):

@@ -58,13 +58,20 @@ def check(out, ref, tol, label):
     for k in ("image_features", "text_features", "logit_scale", "loss", "logits_per_image", "logits_per_text"):
         report[k] = O.l2_rel(out[k], ref[k])
     worst, fails = O.compare_grads(out["grads"], ref["grads"], tol)
-    # d loss / d log-scale = mean_i(s u_i.o_i) - mean_i(A_ii) is a difference of two O(|A_ii|) terms (50x
-    # cancellation in the toy fixtures): its error is bounded relative to those terms, not to the difference
+    # d loss / d log-scale = mean_i(s u_i.o_i) - mean_i(A_ii) is a difference of two O(|A_ii|) terms (50x cancellation in
+    # the toy fixtures).  The RAW relative error is always printed; when it exceeds tol the gradient is accepted only if
+    # its absolute error is within tol of the terms it is the difference of, and the case is flagged EXEMPT in the log
+    # (which modes need it is recorded in DESIGN.md 4 from these lines).
     cond = float(ref["logits_per_image"].diag().abs().mean())
-    dt_err = abs(float(out["grads"]["logit_scale"]) - float(ref["grads"]["logit_scale"]))
-    fails = [f for f in fails if not (f[0] == "logit_scale" and dt_err <= tol * max(cond, abs(float(ref["grads"]["logit_scale"]))))]
+    ref_dt = float(ref["grads"]["logit_scale"])
+    dt_err = abs(float(out["grads"]["logit_scale"]) - ref_dt)
+    dt_raw = dt_err / max(abs(ref_dt), 1e-30)
+    report["dlogit_scale_raw"] = dt_raw
+    if dt_raw > tol and dt_err <= tol * max(cond, abs(ref_dt)):
+        print(f"[{label}] EXEMPT logit_scale gradient: raw rel {dt_raw:.2e} > {tol}, abs err {dt_err:.2e} <= tol * mean|A_ii| = {tol * cond:.2e}")
+        fails = [f for f in fails if f[0] != "logit_scale"]
     print(f"[{label}] " + " ".join(f"{k}={v:.2e}" for k, v in report.items()) + f" grads_worst={worst:.2e}")
-    bad = {k: v for k, v in report.items() if not v <= tol}
+    bad = {k: v for k, v in report.items() if k != "dlogit_scale_raw" and not v <= tol}
     assert not bad, f"{label}: outputs beyond {tol}: {bad}"
     assert not fails, f"{label}: {len(fails)} gradients beyond {tol}: {sorted(fails, key=lambda t: -t[1])[:8]}"
 
