@@ -60,6 +60,7 @@ struct GemmTcArgs {
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
     int exp_flags;                          // MC_GEMM_EXP bits (default 3 since round 2): 1 plain remote arrive, 2 lean MMA issuer loop
+    int epi_bufs, epi_alt_off;              // output staging buffers per epilogue warp (1 or 2) and the byte offset of the second
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
     // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
     // loads a stage's full barrier no longer depends on the second producer warp, so that warp can be lapped by two
@@ -468,6 +469,13 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// staging tile about to be rewritten: with two alternating output buffers per warp only the store issued TWO chunks ago
+// must have finished reading shared memory, so the TMA store of chunk i drains while chunk i + 1 is computed
+__device__ __forceinline__ void bulk_wait_stage(int bufs) {
+    if (bufs > 1) bulk_wait_read1();
+    else bulk_wait_read0();
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -483,7 +491,7 @@ constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C c
 // epilogue's L1 traffic, which ncu showed to be what kept the tensor pipe at 48 % (profiles/r1b_*).
 template <int EPI>
 __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
-                                               uint32_t taddr, uint32_t stage, float bias_m, bool row_ok, long long crow,
+                                               uint32_t taddr, uint32_t stage, uint32_t cstage, float bias_m, bool row_ok, long long crow,
                                                int m_base, int b, int n, int lane, uint32_t zbar, uint32_t zphase,
                                                uint32_t zoff, int pf_n, int pf_m, int pf_b, float& rsum) {
     uint32_t v[32];
@@ -505,15 +513,15 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             if (full) rsum += r.x + r.y;
             else rsum += (n + 2 * i < g.N ? r.x : 0.f) + (n + 2 * i + 1 < g.N ? r.y : 0.f);
         }
-        if (lane == 0) bulk_wait_read0();
+        if (lane == 0) bulk_wait_stage(g.epi_bufs);
         __syncwarp();
-        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+        const uint32_t rowp = cstage + lane * 64, sw = (lane >> 1) & 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_3d(tmC, stage, n, m_base, b);
+            tma_store_3d(tmC, cstage, n, m_base, b);
             bulk_commit();
         }
     } else if constexpr (EPI == EPI_ACT_BWD) {
@@ -556,14 +564,15 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
                 else rsum += (n + 2 * i < g.N ? r.x : 0.f) + (n + 2 * i + 1 < g.N ? r.y : 0.f);
             }
         }
-        if (lane == 0) bulk_wait_read0();
+        if (lane == 0) bulk_wait_stage(g.epi_bufs);
         __syncwarp();
+        const uint32_t crowp = cstage + lane * 64;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sts128(rowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) sts128(crowp + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_3d(tmC, stage, n, m_base, b);
+            tma_store_3d(tmC, cstage, n, m_base, b);
             bulk_commit();
         }
     } else if constexpr (EPI == EPI_ACT_FWD) {
@@ -592,9 +601,9 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
 #pragma unroll
             for (int i = 0; i < 16; ++i) x[i] = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bm);
         }
-        if (lane == 0) bulk_wait_read0();
+        if (lane == 0) bulk_wait_stage(g.epi_bufs);
         __syncwarp();
-        const uint32_t rowp = stage + lane * 64, sw = (lane >> 1) & 3;
+        const uint32_t rowp = cstage + lane * 64, sw = (lane >> 1) & 3;
         if (g.zout != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -612,8 +621,8 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_3d(tmC, stage, n, m_base, b);
-            if (g.zout != nullptr) tma_store_3d(tmZ, stage + 2048, n, m_base, b);
+            tma_store_3d(tmC, cstage, n, m_base, b);
+            if (g.zout != nullptr) tma_store_3d(tmZ, cstage + 2048, n, m_base, b);
             bulk_commit();
         }
     } else if constexpr (EPI == EPI_RESID) {
@@ -663,16 +672,16 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
     } else {  // EPI_PLAIN: fp32 tile, plain store or reduce-add (accumulate / split-K)
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (lane == 0) bulk_wait_read0();
+        if (lane == 0) bulk_wait_stage(g.epi_bufs);
         __syncwarp();
-        const uint32_t rowp = stage + lane * 128, sw = lane & 7;
+        const uint32_t rowp = cstage + lane * 128, sw = lane & 7;
 #pragma unroll
         for (int j = 0; j < 8; ++j) sts128(rowp + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            if (g.accumulate || g.atomic) tma_reduce_add_3d(tmC, stage, n, m_base, b);
-            else tma_store_3d(tmC, stage, n, m_base, b);
+            if (g.accumulate || g.atomic) tma_reduce_add_3d(tmC, cstage, n, m_base, b);
+            else tma_store_3d(tmC, cstage, n, m_base, b);
             bulk_commit();
         }
     }
@@ -1073,7 +1082,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pf_c = half * 32;
             }
         };
-        uint32_t zslot = 0, zphase_bits = 0;
+        uint32_t zslot = 0, zphase_bits = 0, cpar = 0;
         if (stream) {
             pf_settle();
             for (int d = 0; d < g.zdepth; ++d) {
@@ -1111,7 +1120,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     chunk32_trans(g, t_row + c, bias_m, m, row_ok, tc.b, nb);
                 } else if (EPI != EPI_GENERIC && g.tma_epi) {
                     const bool pf_ok = kStream && pf_t < g.num_tiles;
-                    chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
+                    const uint32_t cstage = stage_buf + (cpar ? (uint32_t)g.epi_alt_off : 0u);
+                    if (g.epi_bufs > 1) cpar ^= 1u;
+                    chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, cstage, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
                                         nb, lane, smem_u32(&zin_bar[e][zslot]), (zphase_bits >> zslot) & 1u,
                                         EPI == EPI_RESID ? 0u : 2048u + 2048u * zslot, pf_ok ? pf_n0 + pf_c : -1, pf_m, pf_b, rsum);
                     if (kStream) {
@@ -1435,7 +1446,15 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
                 al16(p->zin, p->ldzin, p->zin_batch_stride, 2);
     static const int zdepth_env = env_int("MC_GEMM_ZDEPTH", 1);
     g.zdepth = (epi == EPI_ACT_BWD && zdepth_env >= 2) ? 2 : 1;
+    // Two alternating OUTPUT staging buffers per epilogue warp (MC_GEMM_EPIBUF=2): the TMA store of chunk i reads its
+    // tile while chunk i + 1 is computed (wait_group.read 1 instead of 0).  Costs 2-4 KB per warp = one ring stage;
+    // the ring runs at 99 % tensor pipe with 3 stages (tools/ubench/ring_handover).
+    static const int epibuf_env = env_int("MC_GEMM_EPIBUF", 1);
+    g.epi_bufs = (epibuf_env >= 2 && epi != EPI_RESID && epi != EPI_GENERIC && epi != EPI_TRANS) ? 2 : 1;
+    const int out_bytes = epi == EPI_PLAIN ? 4096 : (epi == EPI_ACT_FWD ? 4096 : 2048);   // bytes of one output buffer (ACT_FWD: C + Z)
     g.epi_warp_bytes = (int)kEpiWarpBytes + (g.zdepth - 1) * 2048;
+    g.epi_alt_off = g.epi_warp_bytes;
+    if (g.epi_bufs == 2) g.epi_warp_bytes += out_bytes;
     const int epi_bytes = g.tma_epi ? kEpiWarps * g.epi_warp_bytes : 0;
     const int smem_budget = 225 * 1024 - epi_bytes;
     g.stages = smem_budget / g.stage_bytes;

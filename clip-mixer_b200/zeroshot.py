@@ -39,6 +39,109 @@ def zeroshot_logits(model, images: torch.Tensor, W: torch.Tensor) -> torch.Tenso
     return out.mul_(100.0)
 
 
+class ZeroShotScorer:
+    """Config 5 at full fidelity (validation.py:119-134,142-179): ``classes x templates`` prompts (ImageNet: 1000 x 80)
+    -> classifier -> ``100 * f @ W`` -> top-k, with both encoders replayed from CUDA graphs.
+
+    The text encoder runs over chunks of ``classes_per_chunk`` whole classes ([chunk * T, context] token rows); the
+    per-class mean of the L2-normalised prompt embeddings and its re-normalisation (:129-131) are part of the same
+    captured graph, so a 1000-class classifier is ``ceil(1000 / chunk)`` graph replays and no eager kernel.  The image
+    side is one graph per image-batch shape: encode, normalise, scoring GEMM, x100."""
+
+    def __init__(self, model, templates: int, classes_per_chunk: int = 50, use_cuda_graph: bool = True):
+        self.model, self.T, self.chunk, self.use_graph = model, int(templates), int(classes_per_chunk), use_cuda_graph
+        self.E = model._cfg["embed_dim"]
+        self._tg = None          # (graph, static tokens, static out [chunk, E])
+        self._ig = {}            # image batch shape -> (graph, static images, static logits)
+        self.W = None
+
+    def _text_chunk(self, tokens, out):
+        m = self.model
+        m._require_store()
+        m._prepare_weights()
+        ws = m._towers["text"].forward(tokens, m._precision, False)
+        e = ws.u_feat.view(self.chunk, self.T, self.E).mean(dim=1)            # ws.u_feat is already L2-normalised (:129-130)
+        torch.div(e, e.norm(dim=-1, keepdim=True), out=out)                   # :131
+
+    @torch.no_grad()
+    def build_classifier(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens: int [classes, templates, context] on the device.  Returns (and keeps) W [E, classes] fp32."""
+        C, T, ctx = tokens.shape
+        if T != self.T:
+            raise ValueError(f"expected {self.T} templates per class, got {T}")
+        dev = tokens.device
+        Wt = torch.empty(C, self.E, device=dev)
+        if self._tg is None:
+            st = torch.zeros(self.chunk * T, ctx, device=dev, dtype=torch.int64)
+            so = torch.empty(self.chunk, self.E, device=dev)
+            st[:, 0] = 1                                                      # any valid token row for the warm-up
+            graph = None
+            if self.use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._text_chunk(st, so)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._text_chunk(st, so)
+            self._tg = (graph, st, so)
+        graph, st, so = self._tg
+        flat = tokens.reshape(C * T, ctx).to(torch.int64)
+        for c0 in range(0, C, self.chunk):
+            c1 = min(C, c0 + self.chunk)
+            rows = (c1 - c0) * T
+            st[:rows].copy_(flat[c0 * T:c1 * T])
+            if rows < st.shape[0]:
+                st[rows:].copy_(flat[:1].expand(st.shape[0] - rows, ctx))      # ragged last chunk: padding rows, discarded
+            if graph is not None:
+                graph.replay()
+            else:
+                self._text_chunk(st, so)
+            Wt[c0:c1].copy_(so[:c1 - c0])
+        self.W = Wt.t().contiguous()                                          # :133  [E, classes]
+        return self.W
+
+    def _image_batch(self, images, logits):
+        m = self.model
+        m._require_store()
+        m._prepare_weights()
+        ws = m._towers["image"].forward(images, m._precision, False)
+        B, C = images.shape[0], self.W.shape[1]
+        ops.gemm("simt", B, C, self.E, 1, ws.u_feat, MAJOR_K, self.E, 0, self.W, MAJOR_MN, C, 0, logits, C, 0)
+        logits.mul_(100.0)                                                    # :162
+
+    @torch.no_grad()
+    def logits(self, images: torch.Tensor) -> torch.Tensor:
+        """100 * normalise(encode_image(images)) @ W -> [batch, classes]; the returned tensor is reused by the next call."""
+        if self.W is None:
+            raise ValueError("build_classifier first")
+        key = (tuple(images.shape), images.dtype, self.W.data_ptr())
+        if key not in self._ig:
+            si = images.clone()
+            so = torch.empty(images.shape[0], self.W.shape[1], device=images.device)
+            graph = None
+            if self.use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._image_batch(si, so)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._image_batch(si, so)
+            self._ig = {key: (graph, si, so)}
+        graph, si, so = self._ig[key]
+        si.copy_(images, non_blocking=True)
+        if graph is not None:
+            graph.replay()
+        else:
+            self._image_batch(si, so)
+        return so
+
+
 def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)):
     """validation.py:136-139."""
     pred = output.topk(max(topk), 1, True, True)[1].t()

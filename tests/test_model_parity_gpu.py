@@ -253,3 +253,32 @@ def test_zero_shot_scoring_matches_oracle():
     target = ref.argmax(1).to(DEV)
     top1, top5 = accuracy(logits, target)
     assert top1 == 9.0 and top5 == 9.0
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_zero_shot_scorer_batched_graph_matches_oracle(use_graph):
+    """validation.py:119-134,142-179 at full structure (classes x templates, ragged last chunk) through the batched,
+    graph-captured ZeroShotScorer, against the oracle's per-class loop."""
+    from clip_mixer_b200.zeroshot import ZeroShotScorer
+    from oracle import mixer_clip_oracle as O
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    model = _build(cfg, sd, "fp32").eval()
+    classes, templates = 11, 6                                       # 11 classes in chunks of 4: last chunk ragged
+    prompts = torch.stack([O.synthetic_batch(cfg, templates, seed=100 + c)[1] for c in range(classes)])
+    images, _ = O.synthetic_batch(cfg, 9, seed=50)
+    scorer = ZeroShotScorer(model, templates, classes_per_chunk=4, use_cuda_graph=use_graph)
+    W = scorer.build_classifier(prompts.to(DEV))
+    logits = scorer.logits(images.to(DEV)).clone()
+    logits2 = scorer.logits(images.to(DEV))                          # second call replays the captured graph
+    cols = []
+    for c in range(classes):
+        e = O.encode_text(sd, prompts[c])
+        e = e / e.norm(dim=-1, keepdim=True)
+        e = e.mean(0)
+        cols.append(e / e.norm())
+    Wref = torch.stack(cols, 1)
+    f = O.encode_image(sd, images)
+    ref = 100.0 * (f / f.norm(dim=-1, keepdim=True)) @ Wref
+    assert O.l2_rel(W, Wref) <= 1e-5 and O.l2_rel(logits, ref) <= 1e-5
+    assert torch.equal(logits, logits2)

@@ -140,7 +140,7 @@ def test_trainer_resumes_from_accelerate_layout_checkpoint(tmp_path, monkeypatch
     for idx, (images, texts) in enumerate(first.trainLoader):
         if idx == 3:
             break
-        head.append(float(first.stepper.step(images, texts)))
+        head.append(float(first.stepper.step(images.to(DEV), texts.to(DEV))))     # the loader yields HOST batches
     first.save_model(0, 3)
     assert sorted(os.listdir("outputs/checkpoints")) == sorted(
         ["epoch.json", "model.safetensors", "optimizer.bin", "random_states_0.pkl", "scheduler.bin"])

@@ -33,6 +33,19 @@ print(f"ncu launch list: total {tot:.0f} us over {nl} launches (cold-cache, seri
 print(f"{'kernel':46} {'n':>5} {'us':>9} {'share':>6} {'dram_rd_MB':>10} {'dram_wr_MB':>10}")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
     print(f"{k[:46]:46} {len(a['n']):5d} {a['us']:9.1f} {a['us'] / tot * 100:5.1f}% {a['rd']:10.1f} {a['wr']:10.1f}")
+if len(sys.argv) > 2:      # launch_summary.py launches.csv out.json [commit]: the traffic file bench.py stamps roofline.traffic with
+    import json
+    fam = {f: [a for k, a in agg.items() if k.startswith(f)] for f in ("gemm_tc_kernel", "token_mix_kernel")}
+    out = {"kernel": "gemm_tc_kernel (all launches of one B/32 batch-256 training step, fused token-mixing schedule)",
+           "dram_bytes_per_step": sum(a["rd"] + a["wr"] for a in fam["gemm_tc_kernel"]) * 1e6,
+           "launches": sum(len(a["n"]) for a in fam["gemm_tc_kernel"]),
+           "share_of_step": sum(a["us"] for a in fam["gemm_tc_kernel"]) / tot,
+           "source": f"profiles/{sys.argv[1].split('/')[-1]} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum)",
+           "commit": sys.argv[3] if len(sys.argv) > 3 else None,
+           "token_mix_kernel": {"dram_bytes_per_step": sum(a["rd"] + a["wr"] for a in fam["token_mix_kernel"]) * 1e6,
+                                "launches": sum(len(a["n"]) for a in fam["token_mix_kernel"]),
+                                "share_of_step": sum(a["us"] for a in fam["token_mix_kernel"]) / tot}}
+    json.dump(out, open(sys.argv[2], "w"), indent=1)
 for fam in ("gemm_tc_kernel", "token_mix_kernel"):
     f = [a for k, a in agg.items() if k.startswith(fam)]
     if f:
