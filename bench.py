@@ -492,6 +492,27 @@ def main():
                                      "launches": len(big), "ms": t_big * 1e3},
                 "token_mix": tm_roof}
 
+    # ---- measured data-parallel timeline of ONE eager two-stream step (MC_DP_TRACE=1): all-reduce overlap / exposed tail ----
+    dp_timeline = None
+    if world > 1 and dp is not None and dp.reducer.trace is not None:
+        tl_step = FusedTrainStep(model, opt, dp, total_steps=10 ** 6, use_cuda_graph=False, micro_batch=micro)
+        tl_step.sm_split = stepper.sm_split
+        for _ in range(2):
+            tl_step.step(images, texts)
+        barrier()
+        dp.reducer.trace.clear()
+        torch.cuda._sleep(int(2e8))                      # host enqueues the whole step behind a spin kernel
+        origin = torch.cuda.Event(enable_timing=True)
+        origin.record()
+        tl_step.step(images, texts)
+        done = torch.cuda.Event(enable_timing=True)
+        done.record()
+        torch.cuda.synchronize()
+        dp_timeline = dp.reducer.timeline(origin)
+        if dp_timeline is not None:
+            dp_timeline["step_ms"] = round(origin.elapsed_time(done), 3)
+        barrier()
+
     # ---- reductions over ranks ----
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
@@ -518,6 +539,10 @@ def main():
                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0) *
                 ((4.0 / 3.0) if micro is not None else 1.0),     # the two-pass step executes 4 forward-equivalents, not 3
                 "loss": loss_value, "roofline": roof}
+        if dp_timeline is not None:
+            line["dp_timeline_rank0"] = dp_timeline
+        if world > 1:
+            line["nccl_env"] = {k: v for k, v in os.environ.items() if k.startswith("NCCL_") or k.startswith("MC_DP")}
         if not args.no_cpu_baseline and world == 1:
             times = cpu_step_time(args.model, 8, 3, 1)
             t = sum(times) / len(times)

@@ -7,10 +7,11 @@ Differences that follow from the scope:
     a path to a Mixer state dict (or an accelerate-style checkpoint holding one) loads through the
     Mixer-aware ``build_model``;
   * ``jit=True`` is rejected (TorchScript archives of the OpenAI transformer models are out of scope);
-  * ``tokenize`` pads / truncates token id sequences exactly like the reference (SOT first, EOT last,
-    zero padding, int32 result); BPE-encoding raw strings needs the 16e6 vocabulary file, which is
-    not shipped here -- pass token ids, or point ``CLIP_BPE_VOCAB`` at the reference's
-    ``bpe_simple_vocab_16e6.txt.gz`` and use ``clip_mixer_b200.clip.bpe`` (not on the hot path).
+  * ``tokenize`` pads / truncates exactly like the reference (SOT first, EOT last, zero padding, int32
+    result) and accepts token id sequences or raw strings.  Raw strings are BPE-encoded by ``clip/bpe.py``
+    (pinned against the reference tokenizer, tests/golden/bpe.json); the merge table is a data asset of
+    the reference (``bpe_simple_vocab_16e6.txt.gz``), found through ``CLIP_BPE_VOCAB`` or ``baseline/_ref``
+    -- without it raw strings raise and token ids must be passed.
 """
 from __future__ import annotations
 
@@ -78,8 +79,8 @@ def load(name: str, device: Union[str, torch.device] = "cuda" if torch.cuda.is_a
 
 def tokenize(texts: Union[str, List[str], Sequence[Sequence[int]], torch.Tensor], context_length: int = 77,
              truncate: bool = False) -> torch.Tensor:
-    """clip.py:198-238.  Accepts already-encoded token id sequences (without SOT/EOT) or, when a BPE
-    vocabulary is configured, raw strings.  Result: int32 [len(texts), context_length]."""
+    """clip.py:198-238.  Accepts raw strings (BPE-encoded by clip/bpe.py; needs the reference's merge table, see the
+    module docstring) or already-encoded token id sequences (without SOT/EOT).  Result: int32 [len(texts), context_length]."""
     if isinstance(texts, str):
         texts = [texts]
     if isinstance(texts, torch.Tensor):

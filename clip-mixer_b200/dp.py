@@ -57,6 +57,15 @@ class GradBucketReducer:
         self.last_member = {m[-1]: k for k, m in enumerate(members)}   # original index that completes bucket k
         self.pending = []
         self.launched = 0
+        # MC_DP_TRACE=1: CUDA events around every bucket's all-reduce (comm stream) and at the points the compute stream
+        # makes a bucket ready / joins the comm stream - bench.py turns them into the measured timeline of one step
+        # (how much of the all-reduce is hidden behind the backward pass, how long the exposed tail is).
+        import os
+        self.trace = [] if (self.cuda and os.environ.get("MC_DP_TRACE", "0") == "1") else None
+        # MC_DP_BF16=1 (opt-in): buckets travel as bf16 (half the NVLink bytes); the sum is formed in bf16 by NCCL, which
+        # costs one rounding of each gradient element (2^-9 relative) - measured against the oracle by tools/dp_check.py.
+        self.bf16_wire = self.cuda and os.environ.get("MC_DP_BF16", "0") == "1"
+        self._wire = None
 
     def ready(self, original_index: int):
         """Original range ``original_index`` is complete; launch its (merged) bucket if it closes one."""
@@ -66,11 +75,26 @@ class GradBucketReducer:
         b, e = self.buckets[k]
         view = self.flat_g[b:e]
         if self.cuda:
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=self.trace is not None)
             ev.record()
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
-                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+                t0 = t1 = None
+                if self.trace is not None:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record()
+                if self.bf16_wire:
+                    if self._wire is None:
+                        self._wire = torch.empty(max(e_ - b_ for b_, e_ in self.buckets), device=view.device, dtype=torch.bfloat16)
+                    w = self._wire[:e - b]
+                    w.copy_(view)
+                    dist.all_reduce(w, op=dist.ReduceOp.AVG, group=self.group)
+                    view.copy_(w)
+                else:
+                    dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+                if self.trace is not None:
+                    t1.record()
+                    self.trace.append((k, (e - b) * 4, ev, t0, t1))
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
             view.div_(self.world)
@@ -79,8 +103,29 @@ class GradBucketReducer:
     def finish(self):
         """Make the compute stream wait for every launched all-reduce."""
         if self.cuda and self.world > 1:
+            if self.trace is not None:
+                self.join_begin = torch.cuda.Event(enable_timing=True)
+                self.join_begin.record()
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+            if self.trace is not None:
+                self.join_end = torch.cuda.Event(enable_timing=True)
+                self.join_end.record()
         self.launched = 0
+
+    def timeline(self, origin):
+        """After a traced step has been synchronised: per-bucket (ready, start, end) in ms relative to the CUDA event
+        `origin`, the time the compute stream reached the join, and how long it then waited (the exposed tail)."""
+        if not self.trace:
+            return None
+        rows = [{"bucket": k, "MB": round(nbytes / 1e6, 1), "ready_ms": round(origin.elapsed_time(ev), 3),
+                 "start_ms": round(origin.elapsed_time(t0), 3), "end_ms": round(origin.elapsed_time(t1), 3)}
+                for k, nbytes, ev, t0, t1 in self.trace]
+        out = {"buckets": rows, "join_reached_ms": round(origin.elapsed_time(self.join_begin), 3),
+               "join_done_ms": round(origin.elapsed_time(self.join_end), 3),
+               "exposed_tail_ms": round(self.join_begin.elapsed_time(self.join_end), 3),
+               "allreduce_busy_ms": round(sum(r["end_ms"] - r["start_ms"] for r in rows), 3)}
+        self.trace.clear()
+        return out
 
 
 def gather_features(ui: torch.Tensor, ut: torch.Tensor, group=None):

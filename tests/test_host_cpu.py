@@ -218,3 +218,27 @@ def test_sm_split_setting_and_candidates(monkeypatch):
     assert stepper("off")._split_candidates(256) == [None]
     assert stepper("84,64")._split_candidates(256) == [(84, 64)]
     assert stepper("auto", micro=64)._split_candidates(256) == [None]    # micro-batched path runs the towers in turn
+
+
+def test_bpe_tokenizer_matches_reference_golden():
+    """clip.tokenize on raw strings (clip.py:198-238 over simple_tokenizer.py:62-132) against ids produced by the REAL
+    reference tokenizer (tests/golden/bpe.json, oracle/make_golden_bpe.py).  Needs the reference's merge table (a data
+    asset copied to baseline/_ref by build()); skipped where it is absent."""
+    import json
+    import pytest
+    from clip_mixer_b200.clip import bpe, tokenize
+    from clip_mixer_b200._lib import MixerClipError
+    try:
+        bpe.vocab_path()
+    except MixerClipError:
+        pytest.skip("BPE merge table not available")
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bpe.json")))
+    tok = bpe.Tokenizer()
+    for row in fx["rows"]:
+        assert tok.encode(row["text"]) == row["ids"], row["text"]
+        out = tokenize([row["text"]], truncate=True)
+        assert out.dtype == torch.int32 and out.shape == (1, 77)
+        assert out[0].tolist() == row["tokenized_truncate"], row["text"]
+    assert tok.decode(tok.encode("hello world, it's me")) == "hello world , it 's me "
+    with pytest.raises(RuntimeError):
+        tokenize([" ".join(["word"] * 100)])     # too long without truncate (clip.py:235)
