@@ -45,7 +45,7 @@ class TokenMixParams(C.Structure):
     _fields_ = [
         ("B", C.c_int64), ("P", C.c_int64), ("D", C.c_int64),
         ("u", C.c_void_p),
-        ("w1", C.c_void_p), ("ld1", C.c_int64), ("b1", C.c_void_p),
+        ("w1", C.c_void_p), ("ld1", C.c_int64), ("w1t", C.c_void_p), ("ld1t", C.c_int64), ("b1", C.c_void_p),
         ("w2", C.c_void_p), ("ld2", C.c_int64), ("b2", C.c_void_p),
         ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p),
         ("gw1", C.c_void_p), ("ldg1", C.c_int64), ("gw2", C.c_void_p), ("ldg2", C.c_int64), ("gb1", C.c_void_p),
@@ -71,6 +71,7 @@ SIGNATURES = {
     "mc_colsum": [_P, _I32, _I64, _I64, _I64, _P, _P],
     "mc_rowsum": [_P, _I32, _I64, _I64, _I64, _I64, _P, _P],
     "mc_cast_pad": [_P, _I64, _I64, _I64, _P, _I32, _I64, _P],
+    "mc_transpose_bf16": [_P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P],
     "mc_im2col": [_P, _I32, _I64, _I64, _I64, _P, _I32, _P],
     "mc_embed_fwd": [_P, _P, _P, _I64, _I64, _I64, _I64, _P],
     "mc_embed_bwd": [_P, _P, _P, _I64, _I64, _I64, _I64, _P],

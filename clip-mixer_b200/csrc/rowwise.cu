@@ -708,6 +708,38 @@ extern "C" int mc_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t
     return MC_OK;
 }
 
+// Batched transpose of small bf16 matrices: dst[b][c][r] = src[b][r][c] (token-mixing lin1 weights [4P x P] -> W1^T
+// [P x 4P], one matrix per Mixer block; the fused token-mixing kernels then fetch BOTH resident weight tiles with plain
+// TMA tensor loads instead of a 2-byte gather at every launch).  Pad columns of dst (c_ld > rows) are written as zero.
+namespace mc { namespace {
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, long long ld_src, long long src_bs,
+                      __nv_bfloat16* __restrict__ dst, long long ld_dst, long long dst_bs) {
+    const __nv_bfloat16* s = src + (long long)blockIdx.y * src_bs;
+    __nv_bfloat16* d = dst + (long long)blockIdx.y * dst_bs;
+    const long long total = (long long)cols * ld_dst;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / ld_dst), r = (int)(i - (long long)c * ld_dst);       // consecutive threads: consecutive dst elements
+        d[i] = r < rows ? s[(long long)r * ld_src + c] : __float2bfloat16_rn(0.f);
+    }
+}
+} }
+
+extern "C" int mc_transpose_bf16(const void* src, int64_t rows, int64_t cols, int64_t ld_src, int64_t src_batch_stride,
+                                 void* dst, int64_t ld_dst, int64_t dst_batch_stride, int64_t batch, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows == 0 || cols == 0 || batch == 0) return MC_OK;
+    MC_CHECK(ld_src >= cols && ld_dst >= rows, "transpose_bf16: leading dimensions too small");
+    MC_CHECK(batch < 65536, "transpose_bf16: too many matrices");
+    const int64_t total = cols * ld_dst;
+    dim3 grid((unsigned)(ceil_div(total, 256) < 64 ? ceil_div(total, 256) : 64), (unsigned)batch);
+    transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), (int)rows, (int)cols, ld_src,
+                                                    src_batch_stride, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
+                                                    dst_batch_stride);
+    MC_CUDA(cudaGetLastError());
+    return MC_OK;
+}
+
 extern "C" int mc_im2col(const void* image, int32_t image_is_u8, int64_t B, int64_t R, int64_t patch, void* out,
                          int32_t out_dtype, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

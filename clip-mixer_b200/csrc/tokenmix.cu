@@ -76,6 +76,9 @@ struct TmArgs {
     int zpitch;               // TMEM columns between Z and dH inside a working buffer (>= widest segment, multiple of 32)
     int ybufs;                // output tiles in TMEM (2 forward, 1 dgrad)
     int stages;
+    int aug;                  // 1: lin1's bias rides in the up GEMM (needs two spare k-rows, Ppad - P >= 2): U rows P, P+1 are
+                              // constant ones, W1^T rows P, P+1 hold the bf16 hi / lo parts of b1 - the E1 warps add nothing
+    uint32_t u_tx_bytes;      // bytes one TMA load of a U group delivers (aug: P rows, else Ppad rows)
     uint32_t grp_bytes;       // Ppad * 128: one [Ppad x 64] swizzled group of an activation / weight tile
     uint32_t a_grp_bytes;     // group pitch of the U tile in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
     uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2;
@@ -145,84 +148,19 @@ __device__ __forceinline__ float2 tm_gelu_grad_from_s(float2 z, float2 s) {
     return __ffma2_rn(t1, s, s);                 // s + w s (1 - s)
 }
 
-// Weights -> resident swizzled tiles.  Element (p, jl) of a tile lives at
+// Resident weight tiles.  Element (p, jl) of a tile lives at
 //   (jl / 64) * grp_bytes + p * 128 + (((jl % 64) / 8) ^ (p % 8)) * 16 + (jl % 8) * 2
-// which is exactly what TMA's SWIZZLE_128B would produce for a [Ppad x 64] box of a [P x 4P] row-major matrix.
-// Only the hidden slice [jbase, jbase + natoms * 64) is loaded (tile-local column jl = j - jbase).  Called by all
-// threads; contains block-wide barriers.
-constexpr int kWIt = 5;     // per-thread 16-byte chunks of a weight tile: ceil(80 * 5 * 8 / 768) = 5
-
-// Phase 1 of the weight staging: every global load of the thread is issued (one DRAM / L2 round trip for both
-// matrices).  Each thread owns whole 16-byte chunks of the tiles:
-//   w2t[p][jl .. jl+7] = W2[p][jbase + jl ..]   one 16-byte load; consecutive threads walk along j (coalesced)
-//   w1t[p][jl .. jl+7] = W1[jbase + jl + e][p]  eight 2-byte loads; consecutive threads walk along p (coalesced rows of
-//                                               W1, and the 16-byte stores of 8 neighbouring p hit 8 different banks -
-//                                               a scatter of 2-byte stores was 8-16-way bank conflicted: 5 us per launch)
-__device__ __forceinline__ void issue_weight_loads(const TmArgs& g, int jbase, int natoms, uint4 (&t2)[kWIt],
-                                                   unsigned short (&t1)[kWIt][8]) {
-    const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
-#pragma unroll
-    for (int it = 0; it < kWIt; ++it) {
-        const int idx = threadIdx.x + it * blockDim.x;
-        t2[it] = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t1[it][e] = 0;
-        if (idx < total) {
-            {
-                const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-                const int j = jbase + cj * 8;
-                if (p < g.P && j < g.H) t2[it] = *reinterpret_cast<const uint4*>(g.w2 + (long long)p * g.ld2 + j);
-            }
-            {
-                const int cj = idx / g.Ppad, p = idx - cj * g.Ppad;
-                const int j = jbase + cj * 8;
-                if (p < g.P) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (j + e < g.H) t1[it][e] = reinterpret_cast<const unsigned short*>(g.w1)[(long long)(j + e) * g.ld1 + p];
-                }
-            }
-        }
-    }
-}
-
-// Phase 2: registers -> swizzled shared-memory tiles, 16-byte stores only.
-__device__ __forceinline__ void store_weight_tiles(const TmArgs& g, uint32_t w1t, uint32_t w2t, int jbase, int natoms,
-                                                   const uint4 (&t2)[kWIt], const unsigned short (&t1)[kWIt][8]) {
-    const int chunks_per_row = natoms * 8, total = g.Ppad * chunks_per_row;
-#pragma unroll
-    for (int it = 0; it < kWIt; ++it) {
-        const int idx = threadIdx.x + it * blockDim.x;
-        if (idx < total) {
-            {
-                const int p = idx / chunks_per_row, cj = idx - p * chunks_per_row;
-                const int grp = cj >> 3, c = cj & 7, j = jbase + cj * 8;
-                uint32_t v[4] = {t2[it].x, t2[it].y, t2[it].z, t2[it].w};
-                if (j + 8 > g.H) {   // pad elements of the last chunk are not trusted
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (j + e >= g.H) v[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
-                }
-                tm_sts128(w2t + (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4), v[0], v[1], v[2], v[3]);
-            }
-            {
-                const int cj = idx / g.Ppad, p = idx - cj * g.Ppad;
-                const int grp = cj >> 3, c = cj & 7;
-                uint32_t v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = (uint32_t)t1[it][2 * e] | ((uint32_t)t1[it][2 * e + 1] << 16);
-                tm_sts128(w1t + (uint32_t)grp * g.grp_bytes + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4), v[0], v[1], v[2], v[3]);
-            }
-        }
-    }
-}
-
+// which is exactly what TMA's SWIZZLE_128B produces for a [Ppad x 64] box of a [P x 4P] row-major matrix, so both tiles
+// arrive by TMA tensor loads in the prologue (w2t from W2, w1t from the W1^T copy the host refreshes once per step with
+// mc_transpose_bf16); rows >= P and columns >= 4P are zero-filled by TMA.  Round 1 gathered W1^T with 2-byte loads and
+// swizzled both tiles through registers in every launch: 13 k clocks of a 71 k-clock kernel (-DTM_TRACE timeline).
 // MODE: TM_FWD / TM_DGRAD / TM_WGRAD.  TD: compile-time channel count D (0 = run time) - with it every global access of
 // the E2 warps is a single LDG / STG with an immediate offset.
 template <int MODE, int TD>
 __global__ void __launch_bounds__(kTmThreads, 1)
 token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmDY,
-                 const __grid_constant__ CUtensorMap tmX, const TmArgs g) {
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1T,
+                 const __grid_constant__ CUtensorMap tmW2, const TmArgs g) {
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t u_full[kMaxTmStages];
     __shared__ __align__(8) uint64_t u_empty[kMaxTmStages];
@@ -232,6 +170,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __shared__ __align__(8) uint64_t h_empty[kMaxAtoms];
     __shared__ __align__(8) uint64_t y_full[2];
     __shared__ __align__(8) uint64_t y_empty[2];
+    __shared__ __align__(8) uint64_t w_full;
     __shared__ uint32_t tmem_base_smem;
 
 #ifndef MC_DIVERGENT_WARP_IDX
@@ -258,11 +197,8 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const int my_atoms = (my_hpad + 63) / 64;
     const int nseg = (my_hpad + SW - 1) / SW;
 
-    // ---- prologue: (1) global loads of the resident weights in flight, (2) barriers + TMEM, (3) the first activation
-    //      tiles requested through TMA, (4) weights into their swizzled tiles.  One DRAM round trip in total. ----
-    uint4 wt2[kWIt];
-    unsigned short wt1[kWIt][8];
-    issue_weight_loads(g, jbase, my_atoms, wt2, wt1);
+    // ---- prologue: barriers + TMEM, then the resident weights and the first activation tiles are requested through TMA
+    //      (one DRAM / L2 round trip for everything); the MMA issuers wait for the weights on w_full ----
     float b1v[2], b2v = 0.f;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -272,10 +208,13 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     if (MODE == TM_FWD && (int)threadIdx.x < g.P) b2v = g.b2[threadIdx.x];
     if (warp == kProdWarp && lane == 0) {
         tma_prefetch_desc(&tmU);
+        tma_prefetch_desc(&tmW1T);
+        tma_prefetch_desc(&tmW2);
         if (MODE != TM_FWD) tma_prefetch_desc(&tmDY);
         if (MODE == TM_FWD) tma_prefetch_desc(&tmX);
     }
     if (warp == kInitWarp && lane == 0) {
+        mbar_init(smem_u32(&w_full), 1);
         for (int s = 0; s < kMaxTmStages; ++s) {
             mbar_init(smem_u32(&u_full[s]), 1);
             mbar_init(smem_u32(&u_empty[s]), 1);
@@ -306,7 +245,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
         const uint32_t bar = smem_u32(&u_full[st]);
         const uint32_t dst = base + g.off_stage + st * g.stage_bytes;
-        mbar_arrive_expect_tx(bar, (MODE == TM_FWD ? 2u : 4u) * g.grp_bytes);
+        mbar_arrive_expect_tx(bar, 2u * g.u_tx_bytes + (MODE == TM_FWD ? 0u : 2u * g.grp_bytes));
         tma_load_3d(dst, &tmU, bar, d0, 0, b);
         tma_load_3d(dst + g.a_grp_bytes, &tmU, bar, d0 + 64, 0, b);
         if (MODE != TM_FWD) {
@@ -319,30 +258,60 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d0 + 32 * i, 0, b);
         }
     };
-    int npre = 0;      // tiles requested before the weights are staged (one per smem stage)
+    int npre = 0;      // tiles requested in the prologue (one per smem stage)
     if (warp == kProdWarp) {
+        if (lane == 0) {
+            // resident weights: my_atoms groups of [Ppad x 64] per matrix, hidden columns jbase + 64 a ..
+            const uint32_t wb = smem_u32(&w_full);
+            mbar_arrive_expect_tx(wb, 2u * (uint32_t)my_atoms * g.grp_bytes);
+            for (int a = 0; a < my_atoms; ++a) {
+                tma_load_3d(w1t + (uint32_t)a * g.grp_bytes, &tmW1T, wb, jbase + 64 * a, 0, 0);
+                tma_load_3d(w2t + (uint32_t)a * g.grp_bytes, &tmW2, wb, jbase + 64 * a, 0, 0);
+            }
+        }
         for (int t = work0; t < g.num_tiles && npre < g.stages; t += work_stride, ++npre)
             if (lane == 0) issue_tile(t, (uint32_t)npre);
     }
-    store_weight_tiles(g, w1t, w2t, jbase, my_atoms, wt2, wt1);
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int i = threadIdx.x + it * blockDim.x;
         if (i < g.natoms * 64) b1s[i] = b1v[it];
     }
     if (MODE == TM_FWD && (int)threadIdx.x < g.Ppad) b2s[threadIdx.x] = b2v;
-    if (MODE == TM_WGRAD) {
-        // rows Ppad .. 127 of every U group are constant: row Ppad is all ones (its accumulator lane collects
-        // db1 = sum_d dZ1), the others zero.  TMA only ever rewrites rows < Ppad of a group.
+    if (MODE == TM_WGRAD || g.aug) {
+        // Constant rows of every U group, written once (TMA only rewrites the rows of its box: P rows with aug, else Ppad):
+        //   aug:   rows P and P+1 are all ones - with W1^T rows P / P+1 = hi / lo halves of b1 the up GEMM adds the bias;
+        //   WGRAD: row Ppad is all ones (its accumulator lane collects db1 = sum_d dZ1); every other row >= P is zero.
         const uint32_t stage0 = base + g.off_stage;
-        const int rows_c = 128 - g.Ppad;
+        const int r_lo = g.aug ? g.P : g.Ppad, r_hi = MODE == TM_WGRAD ? 128 : g.Ppad;
+        const int rows_c = r_hi - r_lo;
         for (int s = 0; s < g.stages; ++s)
             for (int grp = 0; grp < 2; ++grp)
                 for (int i = threadIdx.x; i < rows_c * 8; i += blockDim.x) {
-                    const int r = g.Ppad + (i >> 3);
-                    const uint32_t v = r == g.Ppad ? 0x3f803f80u : 0u;     // bf16 1.0 pairs
+                    const int r = r_lo + (i >> 3);
+                    const bool one = (g.aug && (r == g.P || r == g.P + 1)) || (MODE == TM_WGRAD && r == g.Ppad);
+                    const uint32_t v = one ? 0x3f803f80u : 0u;     // bf16 1.0 pairs
                     tm_sts128(stage0 + s * g.stage_bytes + grp * g.a_grp_bytes + r * 128 + ((i & 7) << 4), v, v, v, v);
                 }
+    }
+    if (g.aug) {
+        // bias rows of the resident W1^T tile (after its TMA load has landed; rows >= P arrived as zeros)
+        mbar_wait(smem_u32(&w_full), 0u);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int jl = threadIdx.x + it * blockDim.x;
+            if (jl < my_atoms * 64) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(b1v[it]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(b1v[it] - __bfloat162float(hi));
+                const uint32_t col = (uint32_t)(jl >> 6) * g.grp_bytes + (uint32_t)(jl & 7) * 2u;
+                const uint32_t c8 = (uint32_t)((jl & 63) >> 3);
+                const uint32_t p0 = (uint32_t)g.P, p1 = (uint32_t)g.P + 1u;
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(w1t + col + p0 * 128u + ((c8 ^ (p0 & 7u)) << 4)),
+                             "h"(*reinterpret_cast<const unsigned short*>(&hi)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(w1t + col + p1 * 128u + ((c8 ^ (p1 & 7u)) << 4)),
+                             "h"(*reinterpret_cast<const unsigned short*>(&lo)) : "memory");
+            }
+        }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -388,6 +357,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             // descriptor templates: the start-address field (bits 0-13, address >> 4) is added per instruction
             const uint64_t dMNg = make_sdesc_sw128(0u, g.grp_bytes, 1024u);       // MN-major, 64-wide groups grp_bytes apart
             const uint64_t dMNa = make_sdesc_sw128(0u, g.a_grp_bytes, 1024u);     // MN-major U tile
+            mbar_wait(smem_u32(&w_full), 0u);                                     // resident weight tiles have landed
             for (int t = work0; t < g.num_tiles; t += work_stride) {
                 TM_TR(kMmaWarp, 1);
                 mbar_wait(smem_u32(&u_full[st]), ph);
@@ -437,6 +407,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             const uint32_t wdn = MODE == TM_FWD ? w2t : w1t;
             const uint64_t dK = make_sdesc_sw128(0u, 16u, 1024u);                 // K-major operand
             const uint64_t dMNh = make_sdesc_sw128(0u, kAtomBytes, 1024u);        // MN-major view of the H^T / dZ1^T atoms
+            mbar_wait(smem_u32(&w_full), 0u);
             for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
                 if (MODE == TM_WGRAD) {
                     // dW2[p, j] += sum_d dY[p, d] H^T[d, j];  dW1^T[p, j] += sum_d U[p, d] dZ1^T[d, j]   (K = 128 channels);
@@ -529,20 +500,36 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     if (col < my_hpad) {
                         const uint32_t dst = hbuf + a * kAtomBytes + row_off;
                         if (MODE == TM_FWD) {
-                            uint32_t v[32];
-                            tmem_ld32(zcol + rel, v);
+                            // two 16-column halves: the TMEM load of the second half is in flight while the first one is
+                            // turned into bf16 (the MUFU-bound part), so only one load latency per chunk is exposed
+                            uint32_t va[16], vb[16];
+                            tmem_ld16(zcol + rel, va);
                             tmem_ld_wait();
-                            uint32_t o[16];
+                            tmem_ld16(zcol + rel + 16, vb);
+                            auto half = [&](const uint32_t (&v)[16], int hf) {
+                                uint32_t o[8];
+                                if (g.aug) {        // the accumulator already holds W1 u + b1
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float2 bb = *reinterpret_cast<const float2*>(b1s + col + 2 * i);
-                                const float2 z = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
-                                const float2 h = tm_gelu2(z);
-                                o[i] = pack_bf16x2(h.x, h.y);
-                            }
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float2 h = tm_gelu2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+                                        o[i] = pack_bf16x2(h.x, h.y);
+                                    }
+                                } else {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                tm_sts128(dst + (((uint32_t)(par * 4 + jj) ^ sw) << 4), o[4 * jj], o[4 * jj + 1], o[4 * jj + 2], o[4 * jj + 3]);
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float2 bb = *reinterpret_cast<const float2*>(b1s + col + hf * 16 + 2 * i);
+                                        const float2 z = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+                                        const float2 h = tm_gelu2(z);
+                                        o[i] = pack_bf16x2(h.x, h.y);
+                                    }
+                                }
+                                const uint32_t cc = (uint32_t)(par * 4 + hf * 2);
+                                tm_sts128(dst + ((cc ^ sw) << 4), o[0], o[1], o[2], o[3]);
+                                tm_sts128(dst + (((cc + 1) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+                            };
+                            half(va, 0);
+                            tmem_ld_wait();
+                            half(vb, 1);
                         } else {
                             const uint32_t dst2 = h2buf + a * kAtomBytes + row_off;
 #pragma unroll
@@ -554,8 +541,8 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                                 uint32_t o[8], oh[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float2 bb = *reinterpret_cast<const float2*>(b1s + col + hf * 16 + 2 * i);
-                                    const float2 z = __fadd2_rn(make_float2(__uint_as_float(zv[2 * i]), __uint_as_float(zv[2 * i + 1])), bb);
+                                    float2 z = make_float2(__uint_as_float(zv[2 * i]), __uint_as_float(zv[2 * i + 1]));
+                                    if (!g.aug) z = __fadd2_rn(z, *reinterpret_cast<const float2*>(b1s + col + hf * 16 + 2 * i));
                                     const float2 sg = tm_sigmoid2(z);
                                     const float2 gp = tm_gelu_grad_from_s(z, sg);
                                     const float2 dz = __fmul2_rn(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), gp);
@@ -726,14 +713,14 @@ int tm_make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int e
 }
 
 template <int MODE, int TD>
-int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const TmArgs& g, int grid, size_t smem,
-                cudaStream_t stream) {
+int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmW1T,
+                const CUtensorMap& tmW2, const TmArgs& g, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
-    token_mix_kernel<MODE, TD><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, g);
+    token_mix_kernel<MODE, TD><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, tmW1T, tmW2, g);
     MC_CUDA(cudaGetLastError());
 #ifdef TM_TRACE
     {
@@ -752,12 +739,12 @@ int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorM
 }
 
 template <int MODE>
-int tm_launch(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const TmArgs& g, int grid, size_t smem,
-              cudaStream_t stream) {
+int tm_launch(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmW1T,
+              const CUtensorMap& tmW2, const TmArgs& g, int grid, size_t smem, cudaStream_t stream) {
     // the two production widths get their own instantiation (immediate-offset global accesses in the E2 warps)
-    if (MODE != TM_WGRAD && g.D == 768) return tm_launch_t<MODE, 768>(tmU, tmDY, tmX, g, grid, smem, stream);
-    if (MODE != TM_WGRAD && g.D == 512) return tm_launch_t<MODE, 512>(tmU, tmDY, tmX, g, grid, smem, stream);
-    return tm_launch_t<MODE, 0>(tmU, tmDY, tmX, g, grid, smem, stream);
+    if (MODE != TM_WGRAD && g.D == 768) return tm_launch_t<MODE, 768>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
+    if (MODE != TM_WGRAD && g.D == 512) return tm_launch_t<MODE, 512>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
+    return tm_launch_t<MODE, 0>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
 }
 
 int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
@@ -768,6 +755,8 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     MC_CHECK(mc_token_mix_supported(p->P, p->D), "token_mix: unsupported shape P=%lld D=%lld (need P <= 80, D %% 128 == 0)",
              (long long)p->P, (long long)p->D);
     MC_CHECK(p->u && p->w1 && p->w2 && p->b1, "token_mix: null operand");
+    MC_CHECK(p->w1t != nullptr && p->ld1t >= 4 * p->P && p->ld1t % 8 == 0 && (reinterpret_cast<uintptr_t>(p->w1t) & 15) == 0,
+             "token_mix: w1t (W1^T bf16 [P x ld1t], mc_transpose_bf16 of w1; ld1t >= 4P, multiple of 8, 16-byte aligned) is required");
     TmArgs g{};
     g.B = (int)p->B; g.P = (int)p->P; g.D = (int)p->D; g.H = 4 * g.P;
     g.Ppad = round_up_i(g.P, 16);
@@ -778,6 +767,12 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     g.num_tiles = g.B * g.tiles_d;
     g.grp_bytes = (uint32_t)g.Ppad * 128u;
     g.a_grp_bytes = mode == TM_WGRAD ? kAtomBytes : g.grp_bytes;
+    {
+        const char* na = getenv("MC_TM_NO_AUG");       // A/B knob: bias added by the E1 warps as in round 1
+        g.aug = (g.Ppad - g.P >= 2 && !(na != nullptr && atoi(na) != 0)) ? 1 : 0;
+    }
+    const int u_rows = g.aug ? g.P : g.Ppad;
+    g.u_tx_bytes = (uint32_t)u_rows * 128u;
     g.w1 = reinterpret_cast<const __nv_bfloat16*>(p->w1); g.ld1 = (int)p->ld1;
     g.w2 = reinterpret_cast<const __nv_bfloat16*>(p->w2); g.ld2 = (int)p->ld2;
     g.b1 = p->b1; g.b2 = p->b2; g.x = p->x; g.y = p->y;
@@ -850,10 +845,17 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     MC_CHECK(smem <= 226 * 1024, "token_mix: shape does not fit in shared memory");
     MC_CHECK(mode != TM_FWD || p->x != p->y, "token_mix fwd: x and y must not alias");
 
-    CUtensorMap tmU, tmDY, tmX;
+    CUtensorMap tmU, tmDY, tmX, tmW1T, tmW2;
     memset(&tmDY, 0, sizeof(tmDY));
     memset(&tmX, 0, sizeof(tmX));
-    int rc = tm_make_map(&tmU, p->u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.D, g.P, g.B, g.D, (int64_t)g.P * g.D, 64, g.Ppad,
+    // resident weight tiles: [Ppad x 64] swizzled groups of W1^T [P x 4P] and W2 [P x 4P]; OOB rows / columns read as zero
+    int rcw = tm_make_map(&tmW1T, p->w1t, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.H, g.P, 1, p->ld1t, (int64_t)g.P * p->ld1t, 64,
+                          g.Ppad, CU_TENSOR_MAP_SWIZZLE_128B, "w1t");
+    if (rcw != MC_OK) return rcw;
+    rcw = tm_make_map(&tmW2, p->w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.H, g.P, 1, g.ld2, (int64_t)g.P * g.ld2, 64, g.Ppad,
+                      CU_TENSOR_MAP_SWIZZLE_128B, "w2");
+    if (rcw != MC_OK) return rcw;
+    int rc = tm_make_map(&tmU, p->u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.D, g.P, g.B, g.D, (int64_t)g.P * g.D, 64, u_rows,
                          CU_TENSOR_MAP_SWIZZLE_128B, "u");
     if (rc != MC_OK) return rc;
     if (mode != TM_FWD) {
@@ -869,9 +871,9 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     }
     if (mode == TM_DGRAD) MC_CHECK(p->y != nullptr, "token_mix dgrad: null output");
     switch (mode) {
-        case TM_FWD: return tm_launch<TM_FWD>(tmU, tmDY, tmX, g, grid, smem, stream);
-        case TM_DGRAD: return tm_launch<TM_DGRAD>(tmU, tmDY, tmX, g, grid, smem, stream);
-        default: return tm_launch<TM_WGRAD>(tmU, tmDY, tmX, g, grid, smem, stream);
+        case TM_FWD: return tm_launch<TM_FWD>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
+        case TM_DGRAD: return tm_launch<TM_DGRAD>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
+        default: return tm_launch<TM_WGRAD>(tmU, tmDY, tmX, tmW1T, tmW2, g, grid, smem, stream);
     }
 }
 

@@ -136,6 +136,28 @@ class TowerRT:
     def fused_tm(self, prec: Precision) -> bool:
         return prec.engine == "tc" and fused_token_mix_enabled() and ops.token_mix_supported(self.P, self.D)
 
+    def refresh_w1t(self, prec: Precision):
+        """W1^T bf16 copies [L, P, ld1t] of the token-mixing lin1 weights for the fused kernels, whose resident weight
+        tiles are fetched by TMA (csrc/tokenmix.cu).  Refreshed at the start of every forward pass (the weights change
+        once per step): ONE batched launch when the blocks' operands are evenly spaced in the bf16 mirror (they are:
+        every block has the same 12 tensors in the same order), else one launch per block."""
+        P, L = self.P, self.L
+        H = 4 * P
+        self.ld1t = (H + 7) // 8 * 8
+        if getattr(self, "w1t", None) is None or self.w1t.device != self.store.device:
+            self.w1t = torch.zeros(L, P, self.ld1t, device=self.store.device, dtype=torch.bfloat16)
+        ops_ = [self.wop(f"{self.blk}.{i}.token_mix_seq.lin1.weight", prec) for i in range(L)]
+        ptrs = [w.data_ptr() for w, _ in ops_]
+        ld1 = ops_[0][1]
+        step = (ptrs[1] - ptrs[0]) if L > 1 else 0
+        even = all(ld == ld1 for _, ld in ops_) and all(ptrs[i] - ptrs[0] == i * step for i in range(L)) and step % 2 == 0
+        if even and L > 1 and step != 0:
+            # block i lives at ptrs[0] + i * step (step < 0: the flat layout follows the backward order, block L-1 first)
+            ops.transpose_bf16(ops_[0][0], H, P, ld1, step // 2, self.w1t, self.ld1t, P * self.ld1t, L)
+        else:
+            for i, (w, ld) in enumerate(ops_):
+                ops.transpose_bf16(w, H, P, ld, 0, self.w1t[i], self.ld1t, 0, 1)
+
     # ---- forward --------------------------------------------------------------------------------
     def forward(self, inp: torch.Tensor, prec: Precision, save: bool) -> TowerWS:
         B = inp.shape[0]
@@ -170,6 +192,8 @@ class TowerRT:
             ops.embed_fwd(text, self.p["token_embedding.weight"], ws.x[0], B, C, D, V)        # model.py:414
             ops.eot_rows(text, ws.rows, B, C)                                                # model.py:424
 
+        if ws.fused_tm:
+            self.refresh_w1t(prec)
         for i in range(L):
             self._block_fwd(i, ws, prec, save)
 
@@ -203,7 +227,7 @@ class TowerRT:
         if ws.fused_tm:
             # one kernel: both GEMMs, bias, QuickGELU and the residual; the hidden [4P x D] tile never leaves the SM
             ops.token_mix_fwd(B, P, D, u, x, y, w1, ld1, self.bp(i, "token_mix_seq.lin1.bias"), w2, ld2,
-                              self.bp(i, "token_mix_seq.lin2.bias"))
+                              self.bp(i, "token_mix_seq.lin2.bias"), w1t=self.w1t[i], ld1t=self.ld1t)
         else:
             ops.gemm(eng, 4 * P, D, P, B, w1, MAJOR_K, ld1, 0, u, MAJOR_MN, D, P * D, h1, D, 4 * P * D,
                      bias=self.bp(i, "token_mix_seq.lin1.bias"), bias_mode=BIAS_M, zout=z1, ldz=D, z_bs=4 * P * D,
@@ -311,8 +335,8 @@ class TowerRT:
             g2, ldg2 = st.grad2d(pre + "token_mix_seq.lin2.weight")
             b1 = self.bp(i, "token_mix_seq.lin1.bias")
             ops.token_mix_wgrad(B, P, D, u, dcur_a, w1, ld1, b1, w2, ld2, g1, ldg1, g2, ldg2,
-                                G(pre + "token_mix_seq.lin1.bias"))
-            ops.token_mix_dgrad(B, P, D, u, dcur_a, dtmp, w1, ld1, b1, w2, ld2)
+                                G(pre + "token_mix_seq.lin1.bias"), w1t=self.w1t[i], ld1t=self.ld1t)
+            ops.token_mix_dgrad(B, P, D, u, dcur_a, dtmp, w1, ld1, b1, w2, ld2, w1t=self.w1t[i], ld1t=self.ld1t)
         elif prec.recompute_z1:
             # dZ1 = (W2^T dY) * g'(W1 U + b1): the pre-activation is recomputed by a second operand pair of the same
             # GEMM tile (K = P is tiny), nothing was saved for it in the forward pass

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BF16, BIAS_M, BIAS_N, BIAS_NONE, F32, MAJOR_K, MAJOR_MN,
                    GemmParams, MixerClipError, TokenMixParams, check)
 
-__all__ = ["gemm", "set_sm_limit", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
+__all__ = ["gemm", "set_sm_limit", "token_mix_supported", "token_mix_fwd", "token_mix_dgrad", "token_mix_wgrad", "transpose_bf16", "w1_transposed", "ln_fwd", "ln_bwd", "colsum", "rowsum", "cast_pad", "im2col", "embed_fwd", "embed_bwd", "eot_rows",
            "l2norm_fwd", "l2norm_bwd", "head_fwd_bwd", "head_workspace_bytes", "sumsq", "sched_step", "adamw", "device_info",
            "F32", "BF16", "MAJOR_K", "MAJOR_MN", "BIAS_NONE", "BIAS_N", "BIAS_M", "ACT_NONE", "ACT_GELU",
            "ACT_GELU_BWD", "launch_count", "reset_launch_count", "enable_gemm_timing", "collect_gemm_timing"]
@@ -155,13 +155,35 @@ def token_mix_supported(P: int, D: int) -> bool:
     return bool(_lib.load().mc_token_mix_supported(P, D))
 
 
-def _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2):
+def transpose_bf16(src, rows, cols, ld_src, src_bs, dst, ld_dst, dst_bs, batch=1):
+    """dst[b][c][r] = src[b][r][c] for `batch` bf16 matrices (W1^T copies of the token-mixing lin1 weights)."""
+    if src.dtype != torch.bfloat16 or dst.dtype != torch.bfloat16:
+        raise MixerClipError("transpose_bf16: bf16 tensors only")
+    check(_lib.load().mc_transpose_bf16(_ptr(src), rows, cols, ld_src, src_bs, _ptr(dst), ld_dst, dst_bs, batch, _stream()),
+          "mc_transpose_bf16")
+    _count()
+
+
+def w1_transposed(w1, P, ld1):
+    """Stand-alone W1^T [P, ld1t] of one lin1 weight operand [4P, ld1] (tests / tools; the engine keeps per-tower copies)."""
+    H = 4 * P
+    ld1t = (H + 7) // 8 * 8
+    out = torch.empty(P, ld1t, device=w1.device, dtype=torch.bfloat16)
+    transpose_bf16(w1, H, P, ld1, 0, out, ld1t, 0, 1)
+    return out, ld1t
+
+
+def _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t=None, ld1t=0):
     for name, t in (("u", u), ("w1", w1), ("w2", w2)):
         if t.dtype != torch.bfloat16:
             raise MixerClipError(f"token_mix: operand {name} must be bf16, got {t.dtype}")
+    if w1t is None:
+        w1t, ld1t = w1_transposed(w1, P, ld1)
     p = TokenMixParams()
     p.B, p.P, p.D = B, P, D
     p.u, p.w1, p.ld1, p.b1, p.w2, p.ld2 = _ptr(u), _ptr(w1), ld1, _ptr(b1), _ptr(w2), ld2
+    p.w1t, p.ld1t = _ptr(w1t), ld1t
+    p._keep = w1t            # keep the transposed copy alive until the (asynchronous) launch has been enqueued
     return p
 
 
@@ -178,30 +200,30 @@ def _tm_call(fn, p, what, B, P, D):
     _count()
 
 
-def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2):
+def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2, w1t=None, ld1t=0):
     """y = x + W2 g(W1 u + b1) + b2 per sample (model.py:216,220-222), one fused kernel."""
-    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t, ld1t)
     p.b2, p.x, p.y = _ptr(b2), _ptr(x), _ptr(y)
     _tm_call(_lib.load().mc_token_mix_fwd, p, "token_mix_fwd", B, P, D)
 
 
-def token_mix_dgrad(B, P, D, u, dy, du, w1, ld1, b1, w2, ld2):
+def token_mix_dgrad(B, P, D, u, dy, du, w1, ld1, b1, w2, ld2, w1t=None, ld1t=0):
     """du = W1^T ((W2^T dy) * g'(W1 u + b1)) per sample, one fused kernel (dy bf16, du fp32)."""
     if dy.dtype != torch.bfloat16 or du.dtype != torch.float32:
         raise MixerClipError("token_mix_dgrad: dy must be bf16 and du fp32")
-    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t, ld1t)
     p.dy, p.y = _ptr(dy), _ptr(du)
     _tm_call(_lib.load().mc_token_mix_dgrad, p, "token_mix_dgrad", B, P, D)
 
 
-def token_mix_wgrad(B, P, D, u, dy, w1, ld1, b1, w2, ld2, gw1, ldg1, gw2, ldg2, gb1):
+def token_mix_wgrad(B, P, D, u, dy, w1, ld1, b1, w2, ld2, gw1, ldg1, gw2, ldg2, gb1, w1t=None, ld1t=0):
     """gw1 += sum_b dZ1 u^T, gw2 += sum_b dy H1^T, gb1 += rowsum(dZ1); H1 and dZ1 are recomputed on chip."""
     if dy.dtype != torch.bfloat16:
         raise MixerClipError("token_mix_wgrad: dy must be bf16")
     for t in (gw1, gw2, gb1):
         if t.dtype != torch.float32:
             raise MixerClipError("token_mix_wgrad: gradients must be fp32")
-    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2)
+    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t, ld1t)
     p.dy, p.gw1, p.ldg1, p.gw2, p.ldg2, p.gb1 = _ptr(dy), _ptr(gw1), ldg1, _ptr(gw2), ldg2, _ptr(gb1)
     _tm_call(_lib.load().mc_token_mix_wgrad, p, "token_mix_wgrad", B, P, D)
 

@@ -139,6 +139,10 @@ typedef struct mc_token_mix_params {
     const void* u;
     const void* w1;
     int64_t ld1;
+    /* W1^T as its own bf16 matrix [P x ld1t] (ld1t >= 4P, multiple of 8; mc_transpose_bf16 of w1): both resident weight
+     * tiles are then fetched by TMA.  Required. */
+    const void* w1t;
+    int64_t ld1t;
     const float* b1;
     const void* w2;
     int64_t ld2;
@@ -194,6 +198,11 @@ int mc_rowsum(const void* x, int32_t dtype, int64_t rows, int64_t cols, int64_t 
 /* fp32 -> act copy (dst dense), optional pad of the leading dimension (token-mix weights). */
 int mc_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t src_ld, void* dst, int32_t dst_dtype,
                 int64_t dst_ld, void* stream);
+
+/* dst[b][c][r] = src[b][r][c] for `batch` small bf16 matrices [rows x cols] (pitch ld_src) -> [cols x ld_dst], pad columns
+ * r >= rows written as zero: W1^T copies of the token-mixing lin1 weights, refreshed once per step. */
+int mc_transpose_bf16(const void* src, int64_t rows, int64_t cols, int64_t ld_src, int64_t src_batch_stride, void* dst,
+                      int64_t ld_dst, int64_t dst_batch_stride, int64_t batch, void* stream);
 
 /* im2col of the stride==kernel patch convolution, model.py:258,272:
  *   image [B,3,R,R] (fp32, or uint8 with the /255 + Normalize of training.py:115,149 fused) ->

