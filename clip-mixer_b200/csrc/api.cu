@@ -47,6 +47,15 @@ int sm_count() {
     return n & ~1;   // CTA pairs: keep it even
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MC_PDL");
+        v = e ? (atoi(e) != 0) : 0;
+    }
+    return v != 0;
+}
+
 }  // namespace mc
 
 extern "C" int mc_version(void) { return 100; }

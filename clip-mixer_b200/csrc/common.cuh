@@ -39,6 +39,41 @@ void set_last_error(const char* fmt, ...);
 
 int sm_count();
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library executes MC_PDL_PROLOGUE() (griddepcontrol.wait)
+// before its first global-memory access, and the hot kernels (GEMM engine, fused token mixing, LayerNorm) execute
+// pdl_launch_dependents() when a CTA has finished its main loop.  With MC_PDL=1 every launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization: kernel N+1's grid is then launched and its CTAs scheduled (running
+// their barrier / TMEM set-up) while kernel N drains its last stores, instead of paying the full launch latency at every
+// one of the ~360 kernel boundaries of a step.  griddepcontrol.wait returns only when the preceding grid has completed
+// and its memory operations are visible, so the ordering is that of plain stream serialisation; both instructions are
+// no-ops in a kernel launched without the attribute.  (The trigger sits at the END of the main loops on purpose: fired
+// at kernel entry, early CTAs of the dependent grid would squat on the SMs of the OTHER tower's stream.)
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define MC_PDL_PROLOGUE() ::mc::pdl_wait()
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+#define MC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (void)::mc::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+#endif
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------

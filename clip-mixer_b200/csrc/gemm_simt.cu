@@ -28,6 +28,7 @@ struct SimtArgs {
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
+    MC_PDL_PROLOGUE();
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
     const int tiles_m = (g.M + TM - 1) / TM;
@@ -160,7 +161,7 @@ extern "C" int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream_) {
         MC_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)p->M * (size_t)p->N, stream));
     }
     dim3 grid((unsigned)tiles, (unsigned)g.out_batch, (unsigned)g.splits);
-    gemm_simt_kernel<<<grid, 256, 0, stream>>>(g);
+    MC_LAUNCH((gemm_simt_kernel), grid, 256, 0, stream, g);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }

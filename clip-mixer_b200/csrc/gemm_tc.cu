@@ -827,6 +827,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (csize > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // everything above touched only shared / tensor memory and kernel parameters: with programmatic dependent launch it
+    // overlaps the tail of the preceding kernel; global memory is first touched below
+    MC_PDL_PROLOGUE();
 
     if (warp == kProdWarp || (warp == kProdWarpB && g.prod2)) {
         // ===================== TMA producer(s) =====================
@@ -1174,6 +1177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             as ^= 1u;
             if (as == 0) aphase ^= 1u;
         }
+        if (e == 0 && lane == 0) pdl_launch_dependents();   // this CTA's tiles are done: the next kernel's grid may be scheduled
         if (g.rowsum_out != nullptr) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
@@ -1301,13 +1305,15 @@ int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)g.cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, TWO>, tmA, tmB, tmC, tmZ, tmA2, tmB2, g));
     return MC_OK;
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_partial_kernel(const float* __restrict__ ui, const float* __restrict__ ut, const float* __restrict__ ui_all,
                     const float* __restrict__ ut_all, const float* __restrict__ log_scale, long long n, long long N,
                     int E, long long rank, int splits, float* __restrict__ ws) {
+    MC_PDL_PROLOGUE();
     extern __shared__ float sm[];
     const int ldq = E + 4;
     float* Qs = sm;                 // [BR][ldq]
@@ -154,6 +155,7 @@ head_combine_kernel(const float* __restrict__ ui, const float* __restrict__ ut, 
                     int E, long long rank, int splits, const float* __restrict__ ws, float grad_scale,
                     float* __restrict__ loss, float* __restrict__ dui, float* __restrict__ dut,
                     float* __restrict__ dlog_scale) {
+    MC_PDL_PROLOGUE();
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (wid >= 2 * n) return;
@@ -225,10 +227,10 @@ extern "C" int mc_head_fwd_bwd(const float* ui, const float* ut, const float* ui
         attr_set = true;
     }
     dim3 grid((unsigned)ceil_div(n, BR), (unsigned)sp, 2);
-    head_partial_kernel<<<grid, kHeadThreads, smem, stream>>>(ui, ut, ui_all, ut_all, log_scale, n, N, (int)E, rank, sp,
+    MC_LAUNCH((head_partial_kernel), grid, kHeadThreads, smem, stream, ui, ut, ui_all, ut_all, log_scale, n, N, (int)E, rank, sp,
                                                               reinterpret_cast<float*>(workspace));
     MC_CUDA(cudaGetLastError());
-    head_combine_kernel<<<(unsigned)ceil_div(2 * n, 8), 256, 0, stream>>>(ui, ut, ui_all, ut_all, log_scale, n, N, (int)E,
+    MC_LAUNCH((head_combine_kernel), (unsigned)ceil_div(2 * n, 8), 256, 0, stream, ui, ut, ui_all, ut_all, log_scale, n, N, (int)E,
                                                                          rank, sp, reinterpret_cast<const float*>(workspace),
                                                                          grad_scale, loss, dui, dut, dlog_scale);
     MC_CUDA(cudaGetLastError());

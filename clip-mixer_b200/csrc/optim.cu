@@ -15,6 +15,7 @@ __device__ float g_sumsq_partials[4096];
 __device__ unsigned int g_sumsq_ticket = 0;
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    MC_PDL_PROLOGUE();
     __shared__ float red[8];
     __shared__ bool last;
     float s = 0.f;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 __global__ void sched_step_kernel(long long* __restrict__ state, float* __restrict__ hyper, long long first_cycle_steps,
                                   double max_lr, double min_lr, long long warmup_steps, double beta1, double beta2,
                                   double fixed_lr) {
+    MC_PDL_PROLOGUE();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const long long t = state[0] + 1, s = state[1];
     double lr = fixed_lr;
@@ -85,6 +87,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              __nv_bfloat16* __restrict__ pb, const uint8_t* __restrict__ decay_flags, long long n4,
              const float* __restrict__ sumsq, const float* __restrict__ hyper, float grad_mul, float max_norm,
              float beta1, float beta2, float eps, float weight_decay) {
+    MC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2];
@@ -132,7 +135,7 @@ extern "C" int mc_sumsq(const float* g, int64_t n, float* out, void* stream_) {
     int64_t cap = (int64_t)sm_count() * 8;
     if (cap > 4096) cap = 4096;
     if (blocks > cap) blocks = cap;
-    sumsq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, n, out);
+    MC_LAUNCH((sumsq_kernel), (unsigned)blocks, 256, 0, stream, g, n, out);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -142,7 +145,7 @@ extern "C" int mc_sched_step(int64_t* state, float* hyper, int64_t first_cycle_s
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MC_CHECK(state != nullptr && hyper != nullptr, "sched_step: null state / hyper");
     MC_CHECK(fixed_lr >= 0.0 || first_cycle_steps > warmup_steps, "sched_step: first_cycle_steps must exceed warmup_steps");
-    sched_step_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<long long*>(state), hyper, first_cycle_steps, max_lr, min_lr,
+    MC_LAUNCH((sched_step_kernel), 1, 32, 0, stream, reinterpret_cast<long long*>(state), hyper, first_cycle_steps, max_lr, min_lr,
                                             warmup_steps, beta1, beta2, fixed_lr);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
@@ -156,7 +159,7 @@ extern "C" int mc_adamw(float* p, const float* g, float* m, float* v, void* p_bf
     MC_CHECK(n % 64 == 0, "adamw: flat buffers are padded to 64-element chunks (n=%lld)", (long long)n);
     MC_CHECK(hyper != nullptr, "adamw: hyper (device {lr, 1-b1^t, 1-b2^t}) is required");
     const int64_t n4 = n / 4;
-    adamw_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
+    MC_LAUNCH((adamw_kernel), (unsigned)ceil_div(n4, 256), 256, 0, stream, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
                                                                   decay_flags, n4, sumsq, hyper, grad_mul, max_norm, beta1,
                                                                   beta2, eps, weight_decay);
     MC_CUDA(cudaGetLastError());

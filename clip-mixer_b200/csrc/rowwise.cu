@@ -32,6 +32,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long x_row_stride, const int* __
               const float* __restrict__ cls, long long cls_period, const float* __restrict__ gamma,
               const float* __restrict__ beta, void* __restrict__ y, int y_dtype, long long y_row_stride,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D) {
+    MC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -46,6 +47,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long x_row_stride, const int* __
         v[i] = c < D ? ld4(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
+    pdl_launch_dependents();      // this row's loads are in flight; the kernel is one wave or two of short CTAs
     const float mean = warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
@@ -88,6 +90,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
               void* __restrict__ dx_act, int act_dtype, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ colsum_out, float* __restrict__ rowsum_out, long long rowsum_period,
               float* __restrict__ dcls, long long rows, int D) {
+    MC_PDL_PROLOGUE();
     __shared__ float red[kWarpsPerBlock][VPL * 128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4 ag[VPL], ab[VPL], ae[VPL];  // dgamma, dbeta, extra (colsum or class-token grad)
@@ -192,6 +195,7 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
                    float* dx /* dres may alias dx: every element is read, then written, by the same thread */, void* __restrict__ dx_act, int act_dtype, float* __restrict__ rowsum_out,
                    long long rowsum_period, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ colsum_out, long long rows, int D) {
+    MC_PDL_PROLOGUE();
     // Persistent over rows.  The column accumulators (dgamma, dbeta, column sums of dx) live in shared memory,
     // one private copy per warp (lane-owned columns: conflict-free read-modify-write), so the kernel keeps the
     // register footprint of a plain row kernel (full occupancy) and the operands are read from HBM exactly once.
@@ -276,6 +280,7 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
             if (lane == 0) atomicAdd(rowsum_out + row % rowsum_period, rsum);
         }
     }
+    if (threadIdx.x == 0) pdl_launch_dependents();          // rows done; only the column reductions remain
     __syncthreads();
     for (int idx = threadIdx.x; idx < 3 * D; idx += blockDim.x) {
         const int which = idx / D, c = idx - which * D;
@@ -319,6 +324,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, float* __restrict__ out,
                   long long rows_per_block) {
+    MC_PDL_PROLOGUE();
     __shared__ float red[8][32][9];
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const long long c = ((long long)blockIdx.x * 32 + cg) * 8;
@@ -351,6 +357,7 @@ colsum_vec_kernel(const T* __restrict__ x, long long rows, long long cols, long 
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, float* __restrict__ out,
                               long long rows_per_block) {
+    MC_PDL_PROLOGUE();
     const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (c >= cols) return;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -370,6 +377,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, long long
 template <typename T>
 __global__ void rowsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld, long long period,
                               float* __restrict__ out, int vec) {
+    MC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -393,6 +401,7 @@ __global__ void rowsum_kernel(const T* __restrict__ x, long long rows, long long
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, long long cols, long long src_ld,
                                 void* __restrict__ dst, int dst_dtype, long long dst_ld) {
+    MC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * dst_ld) return;
     const long long r = i / dst_ld, c = i % dst_ld;
@@ -409,6 +418,7 @@ __constant__ float kImgStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 template <bool U8>
 __global__ void im2col_kernel(const void* __restrict__ image, long long B, int R, int patch, void* __restrict__ out,
                               int out_dtype) {
+    MC_PDL_PROLOGUE();
     const int g = R / patch;
     const long long Kc = 3ll * patch * patch;
     const long long total4 = B * g * g * Kc / 4;
@@ -438,6 +448,7 @@ __global__ void im2col_kernel(const void* __restrict__ image, long long B, int R
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const long long* __restrict__ text, const float* __restrict__ table, float* __restrict__ x,
                                  long long rows, int W, long long vocab) {
+    MC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -453,6 +464,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ text, const float
 template <int VPL>
 __global__ void embed_bwd_kernel(const long long* __restrict__ text, const float* __restrict__ dx, float* __restrict__ dtable,
                                  long long B, int C, int W, long long vocab) {
+    MC_PDL_PROLOGUE();
     const long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -492,6 +504,7 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ text, const float
 }
 
 __global__ void eot_rows_kernel(const long long* __restrict__ text, int* __restrict__ eot_row, long long B, int C) {
+    MC_PDL_PROLOGUE();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     long long best = text[b * C];
@@ -509,6 +522,7 @@ __global__ void eot_rows_kernel(const long long* __restrict__ text, int* __restr
 template <int VPL>
 __global__ void l2norm_fwd_kernel(const float* __restrict__ f, float* __restrict__ u, float* __restrict__ inv_norm,
                                   long long rows, int E) {
+    MC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -532,6 +546,7 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ f, float* __restrict
 template <int VPL>
 __global__ void l2norm_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, const float* __restrict__ inv_norm,
                                   float* __restrict__ df, void* __restrict__ df_act, int act_dtype, long long rows, int E) {
+    MC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -599,7 +614,7 @@ extern "C" int mc_ln_fwd(const float* x, int64_t x_row_stride, const int32_t* ro
              "ln_fwd: pointers must be 16-byte aligned");
     MC_CHECK(cls == nullptr || cls_period > 0, "ln_fwd: cls_period must be positive");
     const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
-    MC_DISPATCH_VPL(vpl, (ln_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+    MC_DISPATCH_VPL(vpl, (MC_LAUNCH((ln_fwd_kernel<VPL>), grid, kWarpsPerBlock * 32, 0, stream, 
                              x, x_row_stride, row_index, cls, cls_period, gamma, beta, y, y_dtype, y_row_stride, mean,
                              rstd, rows, (int)D)));
     MC_CUDA(cudaGetLastError());
@@ -638,7 +653,7 @@ extern "C" int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, 
                 MC_CUDA(cudaFuncSetAttribute(ln_bwd_rows_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 attr_set = true;
             }
-            ln_bwd_rows_kernel<VPL><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+            MC_LAUNCH((ln_bwd_rows_kernel<VPL>), (unsigned)blocks, kWarpsPerBlock * 32, smem, stream, 
                 dy, x, mean, rstd, gamma, dres, dx, dx_act, act_dtype, rowsum_out, rowsum_period, dgamma, dbeta, colsum_out,
                 rows, (int)D);
         });
@@ -648,7 +663,7 @@ extern "C" int mc_ln_bwd(const float* dy, const float* x, int64_t x_row_stride, 
     int64_t blocks = ceil_div(rows, kWarpsPerBlock);
     const int64_t cap = (int64_t)sm_count() * 2;
     if (blocks > cap) blocks = cap;
-    MC_DISPATCH_VPL(vpl, (ln_bwd_kernel<VPL><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+    MC_DISPATCH_VPL(vpl, (MC_LAUNCH((ln_bwd_kernel<VPL>), (unsigned)blocks, kWarpsPerBlock * 32, 0, stream, 
                              dy, x, x_row_stride, row_index, cls, cls_period, mean, rstd, gamma, dres, dx, dx_row_stride,
                              dx_act, act_dtype, dgamma, dbeta, colsum_out, rowsum_out, rowsum_period, dcls, rows, (int)D)));
     MC_CUDA(cudaGetLastError());
@@ -668,14 +683,14 @@ extern "C" int mc_colsum(const void* x, int32_t dtype, int64_t rows, int64_t col
     dim3 grid((unsigned)col_blocks, (unsigned)ceil_div(rows, rpb));
     if (vec) {
         if (dtype == MC_BF16)
-            colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
+            MC_LAUNCH((colsum_vec_kernel<__nv_bfloat16>), grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
         else
-            colsum_vec_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
+            MC_LAUNCH((colsum_vec_kernel<float>), grid, 256, 0, stream, reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
     } else {
         if (dtype == MC_BF16)
-            colsum_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
+            MC_LAUNCH((colsum_kernel<__nv_bfloat16>), grid, 128, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, out, rpb);
         else
-            colsum_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
+            MC_LAUNCH((colsum_kernel<float>), grid, 128, 0, stream, reinterpret_cast<const float*>(x), rows, cols, ld, out, rpb);
     }
     MC_CUDA(cudaGetLastError());
     return MC_OK;
@@ -690,9 +705,9 @@ extern "C" int mc_rowsum(const void* x, int32_t dtype, int64_t rows, int64_t col
     const int esz = dtype == MC_BF16 ? 2 : 4;
     const int vec = (cols % 8 == 0 && (ld * esz) % 16 == 0 && aligned16(x)) ? 1 : 0;
     if (dtype == MC_BF16)
-        rowsum_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, period, out, vec);
+        MC_LAUNCH((rowsum_kernel<__nv_bfloat16>), grid, kWarpsPerBlock * 32, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld, period, out, vec);
     else
-        rowsum_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(reinterpret_cast<const float*>(x), rows, cols, ld, period, out, vec);
+        MC_LAUNCH((rowsum_kernel<float>), grid, kWarpsPerBlock * 32, 0, stream, reinterpret_cast<const float*>(x), rows, cols, ld, period, out, vec);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -703,7 +718,7 @@ extern "C" int mc_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t
     if (rows == 0 || cols == 0) return MC_OK;
     MC_CHECK(dst_ld >= cols && src_ld >= cols, "cast_pad: leading dimensions smaller than cols");
     const int64_t total = rows * dst_ld;
-    cast_pad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, rows, cols, src_ld, dst, dst_dtype, dst_ld);
+    MC_LAUNCH((cast_pad_kernel), (unsigned)ceil_div(total, 256), 256, 0, stream, src, rows, cols, src_ld, dst, dst_dtype, dst_ld);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -715,6 +730,7 @@ namespace mc { namespace {
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, long long ld_src, long long src_bs,
                       __nv_bfloat16* __restrict__ dst, long long ld_dst, long long dst_bs) {
+    MC_PDL_PROLOGUE();
     const __nv_bfloat16* s = src + (long long)blockIdx.y * src_bs;
     __nv_bfloat16* d = dst + (long long)blockIdx.y * dst_bs;
     const long long total = (long long)cols * ld_dst;
@@ -733,7 +749,7 @@ extern "C" int mc_transpose_bf16(const void* src, int64_t rows, int64_t cols, in
     MC_CHECK(batch < 65536, "transpose_bf16: too many matrices");
     const int64_t total = cols * ld_dst;
     dim3 grid((unsigned)(ceil_div(total, 256) < 64 ? ceil_div(total, 256) : 64), (unsigned)batch);
-    transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), (int)rows, (int)cols, ld_src,
+    MC_LAUNCH((transpose_bf16_kernel), grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(src), (int)rows, (int)cols, ld_src,
                                                     src_batch_stride, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
                                                     dst_batch_stride);
     MC_CUDA(cudaGetLastError());
@@ -751,9 +767,9 @@ extern "C" int mc_im2col(const void* image, int32_t image_is_u8, int64_t B, int6
     const int64_t blocks = ceil_div(total, 256);
     MC_CHECK(blocks < (1ll << 31), "im2col: too large");
     if (image_is_u8)
-        im2col_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(image, B, (int)R, (int)patch, out, out_dtype);
+        MC_LAUNCH((im2col_kernel<true>), (unsigned)blocks, 256, 0, stream, image, B, (int)R, (int)patch, out, out_dtype);
     else
-        im2col_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(image, B, (int)R, (int)patch, out, out_dtype);
+        MC_LAUNCH((im2col_kernel<false>), (unsigned)blocks, 256, 0, stream, image, B, (int)R, (int)patch, out, out_dtype);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -764,7 +780,7 @@ extern "C" int mc_embed_fwd(const int64_t* text, const float* table, float* x, i
     if (B == 0) return MC_OK;
     MC_CHECK(W % 4 == 0, "embed: width must be a multiple of 4");
     const int64_t rows = B * C;
-    embed_fwd_kernel<<<(unsigned)ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(
+    MC_LAUNCH((embed_fwd_kernel), (unsigned)ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream, 
         reinterpret_cast<const long long*>(text), table, x, rows, (int)W, vocab);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
@@ -778,7 +794,7 @@ extern "C" int mc_embed_bwd(const int64_t* text, const float* dx, float* dtable,
     MC_CHECK(vpl > 0 && W % 4 == 0, "embed_bwd: width must be a multiple of 4 and <= 1024");
     MC_CHECK(aligned16(dtable) && aligned16(dx), "embed_bwd: pointers must be 16-byte aligned");
     const unsigned grid = (unsigned)ceil_div(B, kWarpsPerBlock);
-    MC_DISPATCH_VPL(vpl, (embed_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+    MC_DISPATCH_VPL(vpl, (MC_LAUNCH((embed_bwd_kernel<VPL>), grid, kWarpsPerBlock * 32, 0, stream, 
                              reinterpret_cast<const long long*>(text), dx, dtable, B, (int)C, (int)W, vocab)));
     MC_CUDA(cudaGetLastError());
     return MC_OK;
@@ -788,7 +804,7 @@ extern "C" int mc_eot_rows(const int64_t* text, int32_t* eot_row, int64_t B, int
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return MC_OK;
     MC_CHECK(B * C < (1ll << 31), "eot_rows: batch too large");
-    eot_rows_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, stream>>>(reinterpret_cast<const long long*>(text), eot_row, B, (int)C);
+    MC_LAUNCH((eot_rows_kernel), (unsigned)ceil_div(B, 128), 128, 0, stream, reinterpret_cast<const long long*>(text), eot_row, B, (int)C);
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -799,7 +815,7 @@ extern "C" int mc_l2norm_fwd(const float* f, float* u, float* inv_norm, int64_t 
     const int vpl = pick_vpl(E);
     MC_CHECK(vpl > 0 && E % 4 == 0, "l2norm: E must be a multiple of 4 and <= 1024");
     const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
-    MC_DISPATCH_VPL(vpl, (l2norm_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(f, u, inv_norm, rows, (int)E)));
+    MC_DISPATCH_VPL(vpl, (MC_LAUNCH((l2norm_fwd_kernel<VPL>), grid, kWarpsPerBlock * 32, 0, stream, f, u, inv_norm, rows, (int)E)));
     MC_CUDA(cudaGetLastError());
     return MC_OK;
 }
@@ -811,7 +827,7 @@ extern "C" int mc_l2norm_bwd(const float* du, const float* u, const float* inv_n
     const int vpl = pick_vpl(E);
     MC_CHECK(vpl > 0 && E % 4 == 0, "l2norm: E must be a multiple of 4 and <= 1024");
     const unsigned grid = (unsigned)ceil_div(rows, kWarpsPerBlock);
-    MC_DISPATCH_VPL(vpl, (l2norm_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(du, u, inv_norm, df, df_act,
+    MC_DISPATCH_VPL(vpl, (MC_LAUNCH((l2norm_bwd_kernel<VPL>), grid, kWarpsPerBlock * 32, 0, stream, du, u, inv_norm, df, df_act,
                                                                                           act_dtype, rows, (int)E)));
     MC_CUDA(cudaGetLastError());
     return MC_OK;

@@ -199,13 +199,6 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 
     // ---- prologue: barriers + TMEM, then the resident weights and the first activation tiles are requested through TMA
     //      (one DRAM / L2 round trip for everything); the MMA issuers wait for the weights on w_full ----
-    float b1v[2], b2v = 0.f;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int i = threadIdx.x + it * blockDim.x;
-        b1v[it] = (i < g.natoms * 64 && jbase + i < g.H) ? g.b1[jbase + i] : 0.f;
-    }
-    if (MODE == TM_FWD && (int)threadIdx.x < g.P) b2v = g.b2[threadIdx.x];
     if (warp == kProdWarp && lane == 0) {
         tma_prefetch_desc(&tmU);
         tma_prefetch_desc(&tmW1T);
@@ -240,6 +233,14 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         tmem_relinquish();
     }
     __syncthreads();
+    MC_PDL_PROLOGUE();      // first global-memory access is below (see common.cuh)
+    float b1v[2], b2v = 0.f;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = threadIdx.x + it * blockDim.x;
+        b1v[it] = (i < g.natoms * 64 && jbase + i < g.H) ? g.b1[jbase + i] : 0.f;
+    }
+    if (MODE == TM_FWD && (int)threadIdx.x < g.P) b2v = g.b2[threadIdx.x];
     // activation tile loads: also used by the producer loop below
     auto issue_tile = [&](int t, uint32_t st) {
         const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
@@ -578,6 +579,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         }
         if (MODE == TM_WGRAD) {
             // ---- final: accumulators -> global gradients.  Lane = token p (or the ones-row Ppad -> db1) ----
+            if (e == 0 && lane == 0) pdl_launch_dependents();
             mbar_wait_relaxed(smem_u32(&y_full[0]), 0u, 64);
             tc_fence_after();
             const int p = r;
@@ -670,6 +672,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 TM_TR(warp, 3);
                 if (lane == 0) mbar_arrive(smem_u32(&y_empty[yb]));
             }
+            if (e2 == 0 && lane == 0) pdl_launch_dependents();   // last tile of this CTA stored
         }
     }
 
@@ -720,7 +723,7 @@ int tm_launch_t(const CUtensorMap& tmU, const CUtensorMap& tmDY, const CUtensorM
         MC_CUDA(cudaFuncSetAttribute(token_mix_kernel<MODE, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
-    token_mix_kernel<MODE, TD><<<grid, kTmThreads, smem, stream>>>(tmU, tmDY, tmX, tmW1T, tmW2, g);
+    MC_LAUNCH((token_mix_kernel<MODE, TD>), grid, kTmThreads, smem, stream, tmU, tmDY, tmX, tmW1T, tmW2, g);
     MC_CUDA(cudaGetLastError());
 #ifdef TM_TRACE
     {
