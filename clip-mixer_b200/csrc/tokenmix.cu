@@ -415,7 +415,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     // one MMA covers the whole hidden slice (N = up to 128 columns = 2 atoms)
                     const uint32_t u_base = base + g.off_stage + st * g.stage_bytes;
                     const uint32_t dy_base = u_base + 2 * g.a_grp_bytes;
-                    mbar_wait(smem_u32(&h_full[0]), n & 1u);
+                    for (int sg = 0; sg < nseg; ++sg) mbar_wait(smem_u32(&h_full[sg]), n & 1u);   // all segments of the slice
                     TM_TR(kMmaDnWarp, 5);
                     tc_fence_after();
                     const uint32_t idesc_w = make_idesc_bf16(128, my_hpad, 0, 1);
@@ -436,7 +436,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                                 umma_ss(acc1, a_u + 2 * k4, b_dz + 128 * ks, idesc_w, ks > 0 ? 1u : accum0);
                             }
                         }
-                        umma_commit(smem_u32(&h_empty[0]));
+                        for (int sg = 0; sg < nseg; ++sg) umma_commit(smem_u32(&h_empty[sg]));
                         umma_commit(smem_u32(&u_empty[st]));     // the activation tile is dead once these MMAs have read it
                     }
                     if (++st == (uint32_t)g.stages) st = 0;
@@ -809,6 +809,24 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         g.zpitch = round_up_i(widest, 32);
     } else {
         g.SW = 128; g.nbuf = 1; g.zpitch = 128; g.ybufs = 1;
+    }
+    {
+        // Experiment knob MC_TM_SW_{FWD,DGRAD,WGRAD}=64|128: narrower segments with TWO working buffers when the columns
+        // allow it - the up GEMMs of segment s+1 then overlap the E1 pass of segment s, and with 64-column segments the
+        // four E1 groups split into two pairs that work on different segments at the same time instead of in lock-step.
+        static const char* names[3] = {"MC_TM_SW_FWD", "MC_TM_SW_DGRAD", "MC_TM_SW_WGRAD"};
+        const char* v = getenv(names[mode]);
+        const int sw = v ? atoi(v) : 0;
+        if (sw == 64 || sw == 128) {
+            const int per_buf = (mode == TM_FWD ? 1 : 2) * sw;
+            const int fixed = mode == TM_FWD ? 2 * g.Ppad : mode == TM_DGRAD ? g.Ppad : 2 * g.slice_w;
+            if ((g.Hpad + sw - 1) / sw <= kMaxAtoms) {
+                g.SW = sw;
+                g.zpitch = sw;
+                g.nbuf = (2 * per_buf + fixed <= 512) ? 2 : 1;
+                MC_CHECK(g.nbuf * per_buf + fixed <= 512, "token_mix: MC_TM_SW does not fit in tensor memory");
+            }
+        }
     }
     MC_CHECK(g.SW >= 64 && g.SW <= 256, "token_mix: bad segment width");
     if (mode == TM_WGRAD) {

@@ -25,6 +25,10 @@ SHAPES = {
     "tok_du": (P, D, 4 * P, B, 1, 1, "tok_plain"),
     "txt_lin3": (B * 77, 2048, 512, 1, 0, 0, "act_fwd"),
     "txt_lin4": (B * 77, 512, 2048, 1, 0, 0, "resid"),
+    "txt_dz2": (B * 77, 2048, 512, 1, 0, 1, "act_bwd"),
+    "txt_dv": (B * 77, 512, 2048, 1, 0, 1, "plain"),
+    "txt_dw3": (2048, 512, B * 77, 1, 1, 1, "acc"),
+    "txt_dw4": (512, 2048, B * 77, 1, 1, 1, "acc"),
 }
 
 

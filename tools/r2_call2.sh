@@ -16,6 +16,10 @@ for cfg in "MC_GEMM_EPIBUF=1" "MC_GEMM_EPIBUF=2"; do
   echo "== $cfg" >> gpurun_out/r2_epibuf.txt
   env $cfg timeout 120 python tools/gemm_bench.py lin3 lin4 dz2 dv dw3 txt_lin3 txt_lin4 >> gpurun_out/r2_epibuf.txt 2>&1
 done
+for bn in 0 128 192 224; do
+  echo "== text-tower shapes, MC_GEMM_BN=$bn (0 = cost model)" >> gpurun_out/r2_epibuf.txt
+  env MC_GEMM_BN=$bn MC_GEMM_DEBUG=0 timeout 120 python tools/gemm_bench.py txt_lin3 txt_lin4 txt_dz2 txt_dv txt_dw3 txt_dw4 lin3 lin4 >> gpurun_out/r2_epibuf.txt 2>&1
+done
 env MC_GEMM_EPIBUF=2 timeout 200 python -m pytest tests/test_gemm_gpu.py -x -q 2>&1 | tail -2 >> gpurun_out/r2_epibuf.txt
 STEPS=15 bash tools/env_sweep.sh "MC_GEMM_EPIBUF=1" "MC_GEMM_EPIBUF=2" "MC_PDL=1" "MC_PDL=1 MC_GEMM_EPIBUF=2" "MC_PDL=0" >> gpurun_out/r2_epibuf.txt 2>&1
 MC_PDL=1 timeout 300 python -m pytest tests/test_train_step_gpu.py tests/test_model_parity_gpu.py -x -q 2>&1 | tail -2 >> gpurun_out/r2_epibuf.txt
