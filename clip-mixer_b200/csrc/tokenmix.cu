@@ -92,6 +92,7 @@ struct TmArgs {
     float* y;
     // WGRAD: the hidden units are dealt to CTAs in slices of slice_w columns
     int nslices, slice_w;
+    int slice_cta0[5];        // CTAs [slice_cta0[s], slice_cta0[s+1]) work on hidden slice s (wider slices get more CTAs)
     float* gw1;               // [4P, ldg1] fp32, +=
     int ldg1;
     float* gw2;               // [P, ldg2] fp32, +=
@@ -187,10 +188,15 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     float* b2s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b2);
     const int SW = g.SW;      // hidden columns per pipeline segment (multiple of 64)
     // WGRAD: CTAs are dealt round-robin to the hidden slices; every slice walks over all tiles
-    const int slice = MODE == TM_WGRAD ? (int)(blockIdx.x % g.nslices) : 0;
+    int slice = 0;
+    if (MODE == TM_WGRAD) {
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+            if (q < g.nslices && (int)blockIdx.x >= g.slice_cta0[q]) slice = q;
+    }
     const int jbase = MODE == TM_WGRAD ? slice * g.slice_w : 0;
-    const int work0 = MODE == TM_WGRAD ? (int)(blockIdx.x / g.nslices) : (int)blockIdx.x;
-    const int work_stride = MODE == TM_WGRAD ? (int)(gridDim.x / g.nslices) : (int)gridDim.x;
+    const int work0 = MODE == TM_WGRAD ? (int)blockIdx.x - g.slice_cta0[slice] : (int)blockIdx.x;
+    const int work_stride = MODE == TM_WGRAD ? g.slice_cta0[slice + 1] - g.slice_cta0[slice] : (int)gridDim.x;
     // hidden columns handled by this CTA (tile-local: column c <-> hidden unit jbase + c)
     int my_hpad = g.Hpad;
     if (MODE == TM_WGRAD) my_hpad = g.Hpad - jbase < g.slice_w ? g.Hpad - jbase : g.slice_w;
@@ -834,8 +840,34 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         natoms_smem = g.slice_w / 64;
         MC_CHECK(p->gw1 && p->gw2 && p->gb1 && p->dy, "token_mix wgrad: null operand");
         g.gw1 = p->gw1; g.ldg1 = (int)p->ldg1; g.gw2 = p->gw2; g.ldg2 = (int)p->ldg2; g.gb1 = p->gb1;
-        grid = sms / g.nslices * g.nslices;
+        MC_CHECK(g.nslices <= 4, "token_mix wgrad: hidden width too large");
+        // CTAs per slice in proportion to the slice's cost per tile (the last slice is narrower: 208 = 128 + 80 columns,
+        // 320 = 128 + 128 + 64): every slice walks over ALL tiles, so with equal shares the wide slices set the time.
+        // Cost per tile ~ fixed hand-over chain + E1 / MMA work proportional to the width (trace: 0.3 + 0.7 w / 128).
+        grid = sms;
         if (grid > g.num_tiles * g.nslices) grid = g.num_tiles * g.nslices;
+        {
+            double cost[4], tot = 0.0;
+            for (int q = 0; q < g.nslices; ++q) {
+                const int w = g.Hpad - q * g.slice_w < g.slice_w ? g.Hpad - q * g.slice_w : g.slice_w;
+                cost[q] = 0.3 + 0.7 * w / 128.0;
+                tot += cost[q];
+            }
+            const char* eq = getenv("MC_TM_WGRAD_EQUAL");
+            int used = 0;
+            g.slice_cta0[0] = 0;
+            for (int q = 0; q < g.nslices; ++q) {
+                int n = (eq != nullptr && atoi(eq) != 0) ? grid / g.nslices : (int)(grid * cost[q] / tot + 0.5);
+                const int reserve = g.nslices - 1 - q;                    // every later slice needs at least one CTA
+                if (n > grid - used - reserve) n = grid - used - reserve;
+                if (n < 1) n = 1;
+                if (q == g.nslices - 1 && !(eq != nullptr && atoi(eq) != 0)) n = grid - used;
+                used += n;
+                g.slice_cta0[q + 1] = used;
+            }
+            MC_CHECK(g.slice_cta0[g.nslices] >= g.nslices && g.slice_cta0[g.nslices] <= sms, "token_mix wgrad: bad CTA split");
+            grid = g.slice_cta0[g.nslices];
+        }
     }
     // shared memory plan (all offsets multiples of 1024)
     uint32_t off = 0;

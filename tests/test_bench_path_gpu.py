@@ -156,20 +156,22 @@ def test_graph_replay_without_host_sync_keeps_the_schedule():
     steps = 12
     image, text = O.synthetic_batch(cfg, 8, seed=1)
     image, text = image.to(DEV), text.to(DEV)
-    finals = []
+    finals, traces = [], []
     for use_graph in (False, True):
         model = _model(cfg, sd, "fp32")
         st = FusedTrainStep(model, total_steps=40, warmup_steps=2, use_cuda_graph=use_graph)
+        losses = []
         if use_graph:
-            st.step(image, text)                       # capture happens here (synchronises); the rest runs unsynchronised
+            losses.append(st.step(image, text).clone())   # capture happens here (synchronises); the rest runs unsynchronised
             torch.cuda._sleep(int(5e8))                # keep the GPU busy so the host really runs ahead of it
             for _ in range(steps - 1):
-                st.step(image, text)
+                losses.append(st.step(image, text).clone())
         else:
             for _ in range(steps):
-                st.step(image, text)
+                losses.append(st.step(image, text).clone())
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
+        traces.append([round(float(l), 6) for l in losses])
         assert st.opt.state.tolist() == [steps, steps] and st.opt.t == steps and st.sched_step == steps
         lr_last = cosine_warmup_lr(steps - 1, 40, 5e-4, 5e-6, 2)
         hy = st.opt.hyper.tolist()
@@ -182,7 +184,7 @@ def test_graph_replay_without_host_sync_keeps_the_schedule():
         den = float(upd0.norm())
         if den > 1e-12:
             worst = max(worst, float((upd1 - upd0).norm()) / den)
-    print(f"[no-sync graph vs synced eager, {steps} steps] worst update difference {worst:.2e}")
+    print(f"[no-sync graph vs synced eager, {steps} steps] worst update difference {worst:.2e}\n  eager losses {traces[0]}\n  graph losses {traces[1]}")
     assert worst <= 5e-3, worst
 
 
