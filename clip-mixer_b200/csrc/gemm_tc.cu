@@ -481,6 +481,20 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// The epilogue's TMA-loaded input slot is re-armed (overwritten by the next TMA load) right after it has been read.
+// "Read" must mean the ld.shared results have ARRIVED: the loads are asynchronous, and with a provably converged warp
+// the compiler drops the WARPSYNC of __syncwarp(), so nothing else sits between the LDS instructions and lane 0's
+// UTMALDG.  A real instruction that consumes the last register of every load makes the warp wait on their scoreboards
+// (round 2: sporadic 16-byte pieces of stale / next-chunk data in the residual and GELU-backward epilogues, 8-12 k wrong
+// elements per GEMM when the grid covered a share of the SMs - found by the 256-sample parity test).
+__device__ __forceinline__ void wait_for_loaded(uint32_t sink_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    // volatile store of a value derived from every load: ptxas cannot drop it (a plain xor chain with an unused result
+    // is dead code to ptxas even inside asm volatile), and it cannot issue before the loads' scoreboards clear
+    asm volatile("{\n\t.reg .b32 t;\n\txor.b32 t, %1, %2;\n\txor.b32 t, t, %3;\n\txor.b32 t, t, %4;\n\t"
+                 "st.volatile.shared.b32 [%0], t;\n\t}"
+                 ::"r"(sink_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 constexpr int kChunkStride = 32 * (kEpiWarps / 4);   // columns between consecutive chunks of one epilogue warp
 constexpr uint32_t kEpiWarpBytes = 4096;  // one 32x32 fp32 chunk, or a bf16 C chunk (2 KB) + an fp16 Z chunk (2 KB); +2 KB per extra Z slot
 
@@ -493,7 +507,8 @@ template <int EPI>
 __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtensorMap* tmC, const CUtensorMap* tmZ,
                                                uint32_t taddr, uint32_t stage, uint32_t cstage, float bias_m, bool row_ok, long long crow,
                                                int m_base, int b, int n, int lane, uint32_t zbar, uint32_t zphase,
-                                               uint32_t zoff, int pf_n, int pf_m, int pf_b, float& rsum) {
+                                               uint32_t zoff, int pf_n, int pf_m, int pf_b, float& rsum,
+                                               [[maybe_unused]] uint32_t sink_addr) {
     uint32_t v[32];
     [[maybe_unused]] const bool full = n + 32 <= g.N;
     if constexpr (EPI == EPI_ACT_BWD_DUAL) {
@@ -536,6 +551,7 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(z[4 * j]), "=r"(z[4 * j + 1]), "=r"(z[4 * j + 2]), "=r"(z[4 * j + 3])
                          : "r"(rowp + zoff + ((j ^ sw) << 4)));
+        wait_for_loaded(sink_addr, z[3], z[7], z[11], z[15]);
         __syncwarp();
         if (lane == 0 && pf_n >= 0) {
             mbar_arrive_expect_tx(zbar, 2048);
@@ -636,6 +652,7 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
                          : "r"(rowp + ((j ^ sw) << 4)));
+        wait_for_loaded(sink_addr, r[3] ^ r[7], r[11] ^ r[15], r[19] ^ r[23], r[27] ^ r[31]);
         __syncwarp();
         if (lane == 0 && pf_n >= 0) {
             mbar_arrive_expect_tx(zbar, 4096);
@@ -767,6 +784,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ __align__(8) uint64_t zin_bar[kEpiWarps][2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ uint32_t epi_sink[kEpiWarps];      // see wait_for_loaded()
 
     // A role index the compiler can prove warp-uniform turns the role branches into uniform control flow, so the
     // producer / issuer / epilogue loops keep their counters, barrier addresses and descriptors in uniform registers:
@@ -1127,7 +1145,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (g.epi_bufs > 1) cpar ^= 1u;
                     chunk32_staged<EPI>(g, &tmC, &tmZ, t_row + c, stage_buf, cstage, bias_m, row_ok, crow, tc.tm * BM + q * 32, tc.b,
                                         nb, lane, smem_u32(&zin_bar[e][zslot]), (zphase_bits >> zslot) & 1u,
-                                        EPI == EPI_RESID ? 0u : 2048u + 2048u * zslot, pf_ok ? pf_n0 + pf_c : -1, pf_m, pf_b, rsum);
+                                        EPI == EPI_RESID ? 0u : 2048u + 2048u * zslot, pf_ok ? pf_n0 + pf_c : -1, pf_m, pf_b, rsum,
+                                        smem_u32(&epi_sink[e]));
                     if (kStream) {
                         zphase_bits ^= 1u << zslot;
                         if (++zslot == (uint32_t)g.zdepth) zslot = 0;

@@ -859,9 +859,10 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
             for (int q = 0; q < g.nslices; ++q) {
                 int n = (eq != nullptr && atoi(eq) != 0) ? grid / g.nslices : (int)(grid * cost[q] / tot + 0.5);
                 const int reserve = g.nslices - 1 - q;                    // every later slice needs at least one CTA
-                if (n > grid - used - reserve) n = grid - used - reserve;
-                if (n < 1) n = 1;
                 if (q == g.nslices - 1 && !(eq != nullptr && atoi(eq) != 0)) n = grid - used;
+                if (n > grid - used - reserve) n = grid - used - reserve;
+                if (n > g.num_tiles) n = g.num_tiles;                     // a CTA without a tile would flush an unwritten accumulator
+                if (n < 1) n = 1;
                 used += n;
                 g.slice_cta0[q + 1] = used;
             }

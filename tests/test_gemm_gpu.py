@@ -310,3 +310,22 @@ def test_gemm_tc_recompute_pair():
         scale = math.sqrt(K) + 1
         assert ((C.double() - ref).abs().max() / scale).item() <= 2e-2
         assert ((rs.double() - ref.sum((0, 2))).abs().max() / (scale * math.sqrt(N * batch))).item() <= 3e-3
+
+
+@pytest.mark.parametrize("sm_limit", [0, 48, 80, 84, 64])
+def test_gemm_tc_streamed_epilogues_on_a_share_of_the_sms(sm_limit):
+    """Regression (round 2): the residual (lin4) and GELU-backward (dZ2) epilogues re-arm the TMA-loaded input slot right
+    after reading it; without waiting for the ld.shared results, the next chunk's data could land first (16-byte pieces
+    of wrong residual / pre-activation, sporadic, far more frequent when the grid covers a share of the SMs as in the
+    two-stream training step).  Shapes of a 64-sample step (odd numbers of 128-row tiles), several SM shares."""
+    ops = _ops()
+    ops.set_sm_limit(sm_limit)
+    try:
+        run_case("tc", 50 * 64, 768, 3072, bias_mode=1, residual=True)                       # image lin4
+        run_case("tc", 50 * 64, 3072, 768, b_major=1, act=2, c_bf16=True)                    # image dZ2
+        run_case("tc", 77 * 64, 512, 2048, bias_mode=1, residual=True)                       # text lin4
+        run_case("tc", 77 * 64, 2048, 512, b_major=1, act=2, c_bf16=True)                    # text dZ2
+        run_case("tc", 50 * 64, 3072, 768, bias_mode=1, act=1, zout=True, c_bf16=True)       # image lin3
+        run_case("tc", 768, 3072, 50 * 64, a_major=1, b_major=1, accumulate=True, split_k=0)  # dW4
+    finally:
+        ops.set_sm_limit(0)

@@ -20,6 +20,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--eager", action="store_true", help="single-stream eager schedule instead of the captured graph")
+    ap.add_argument("--no-graph", action="store_true", help="two-stream schedule, not captured")
+    ap.add_argument("--single-stream", action="store_true", help="captured graph of the single-stream schedule")
+    ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--reference", action="store_true", help="the reference's own bf16-autocast path instead of ours")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -36,10 +39,23 @@ def main():
         loss, grads = T._reference_bf16_autocast_grads(img, texts, sd)
     else:
         from clip_mixer_b200.training import FusedTrainStep
-        st = FusedTrainStep(model, total_steps=10 ** 6, use_cuda_graph=not a.eager, overlap_towers=not a.eager)
-        loss = float(st.step(images_u8.to("cuda:0"), texts.to("cuda:0")))
-        torch.cuda.synchronize()
-        grads = {k: p.grad.detach().float().cpu().clone() for k, p in model.named_parameters()}
+        st = FusedTrainStep(model, total_steps=10 ** 6, use_cuda_graph=not (a.eager or a.no_graph),
+                            overlap_towers=not (a.eager or a.single_stream))
+        sd0 = {k: p.detach().clone() for k, p in model.named_parameters()}
+        for rep in range(a.repeat):
+            if rep:                                  # same weights again: run-to-run spread of one configuration
+                with torch.no_grad():
+                    for k, p in model.named_parameters():
+                        p.copy_(sd0[k])
+                model.mark_weights_dirty()
+                if model._store.flat_w16 is not None:
+                    model._store.refresh_mirror(force=True)
+            loss = float(st.step(images_u8.to("cuda:0"), texts.to("cuda:0")))
+            torch.cuda.synchronize()
+            grads = {k: p.grad.detach().float().cpu().clone() for k, p in model.named_parameters()}
+            if rep + 1 < a.repeat:
+                e_, m_, w_ = T._grad_errors(grads, truth)
+                print(json.dumps({"tag": a.tag, "rep": rep, "sm_split": st.sm_split, "median": m_, "whole_model": w_}), flush=True)
     errs, median, whole = T._grad_errors(grads, truth)
     by = {}
     for e, k in errs:
@@ -48,7 +64,7 @@ def main():
     groups = {k: round(sum(v) / len(v), 4) for k, v in sorted(by.items())}
     print(json.dumps({"tag": a.tag, "batch": a.batch, "reference": a.reference, "eager": a.eager,
                       "env": {k: v for k, v in os.environ.items() if k.startswith("MC_")},
-                      "loss_rel": abs(loss - float(truth["loss"])) / float(truth["loss"]), "worst": errs[0][0], "median": median,
+                      "sm_split": None if a.reference else st.sm_split, "loss_rel": abs(loss - float(truth["loss"])) / float(truth["loss"]), "worst": errs[0][0], "median": median,
                       "whole_model": whole, "mean_by_kind": groups}), flush=True)
 
 
