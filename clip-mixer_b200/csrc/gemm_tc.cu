@@ -60,6 +60,7 @@ struct GemmTcArgs {
     int two_cta;                            // tcgen05 cta_group::2: the pair computes a 256 x BN tile, B split in halves
     int prod2;                              // second producer warp issues the B operand
     int exp_flags;                          // MC_GEMM_EXP bits (default 3 since round 2): 1 plain remote arrive, 2 lean MMA issuer loop
+    int l2pf_a, l2pf_b;                     // k-blocks of L2 prefetch distance for the A / B operand (0 = off)
     int epi_bufs, epi_alt_off;              // output staging buffers per epilogue warp (1 or 2) and the byte offset of the second
     int zdepth, epi_warp_bytes;             // lookahead of the epilogue's TMA-loaded inputs (chunks), staging bytes per epilogue warp
     // MC_GEMM_DEBUG_SKIP bits (timing experiments, wrong results): 1 no TMA loads, 2 no MMAs, 4 no epilogue.  Without the
@@ -704,6 +705,13 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
     }
 }
 
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -866,6 +874,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = is_issuer != 0;
         uint32_t stage = 0, phase = 0;
         const uint16_t mc_mask = (uint16_t)((1u << csize) - 1u);
+        // Rolling L2 prefetch (MC_GEMM_L2PF): a second cursor walks the same (tile, k-block) sequence `dist` k-blocks ahead
+        // of the loads and asks L2 for the boxes of the operands that stream from DRAM (activations).  The ring covers
+        // ~2.5 k clocks of MMA work, less than a loaded DRAM round trip, so without it the issuer waits on `full`.
+        const int pf_dist = do_a ? g.l2pf_a : g.l2pf_b;
+        int pf_t = work0, pf_kb = 0;
+        bool pf_valid = false;
+        TileCoord pfc{};
+        auto pf_tile = [&]() {
+            pf_valid = pf_dist > 0 && pf_t < g.num_tiles;
+            if (pf_valid) {
+                pfc = decode_tile(g, pf_t, cta_rank);
+                pf_kb = pfc.kb_begin;
+            }
+        };
+        auto pf_step = [&]() {
+            if (!pf_valid) return;
+            int pb = pfc.b, pk = pf_kb * BK;
+            if (g.k_spans_batch) {
+                pb = pf_kb / g.kb_per_batch;
+                pk = (pf_kb - pb * g.kb_per_batch) * BK;
+            }
+            if (issuer) {
+                if (do_a && g.l2pf_a) {
+                    const int pm0 = pfc.tm * BM, pba = g.a_batched ? pb : 0;
+                    if (g.a_mn) {
+                        tma_prefetch_l2_3d(&tmA, pm0, pk, pba);
+                        tma_prefetch_l2_3d(&tmA, pm0 + 64, pk, pba);
+                    } else {
+                        tma_prefetch_l2_3d(&tmA, pk, pm0, pba);
+                    }
+                }
+                if (do_b && g.l2pf_b) {
+                    const int pbb = g.b_batched ? pb : 0;
+                    const int cols = TWO ? g.BN / 2 : g.BN;
+                    const int pn0 = pfc.tn * g.BN + (TWO ? cta_rank * (g.BN / 2) : 0);
+                    if (g.b_mn) {
+                        for (int j = 0; j * 64 < cols; ++j) tma_prefetch_l2_3d(&tmB, pn0 + j * 64, pk, pbb);
+                    } else if (TWO || csize == 1) {
+                        tma_prefetch_l2_3d(&tmB, pk, pn0, pbb);
+                    }
+                }
+            }
+            if (++pf_kb >= pfc.kb_end) {
+                pf_t += work_stride;
+                pf_tile();
+            }
+        };
+        pf_tile();
+        for (int d = 0; d < pf_dist; ++d) pf_step();
         for (int t = work0; t < g.num_tiles; t += work_stride) {
             const TileCoord tc = decode_tile(g, t, cta_rank);
             const int m0 = tc.tm * BM, n0 = tc.tn * g.BN;
@@ -875,6 +932,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     bb = kb / g.kb_per_batch;
                     kk = (kb - bb * g.kb_per_batch) * BK;
                 }
+                pf_step();
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
                 const uint32_t bar = smem_u32(&full_bar[stage]);
                 const uint32_t a_dst = tiles_base + stage * g.stage_bytes;
@@ -1430,6 +1488,14 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     static const int prod2 = env_int("MC_GEMM_PROD2", 1);
     g.prod2 = prod2 ? 1 : 0;
     g.dbg_skip = env_int("MC_GEMM_DEBUG_SKIP", 0);
+    {
+        // Operands that stream from DRAM: the A operand of every GEMM (activations), and B too in the weight-gradient
+        // GEMMs (both operands are activations).  Weights (the B operand of forward / dgrad, 1-5 MB) stay L2-resident.
+        static const int l2pf = env_int("MC_GEMM_L2PF", 0);
+        g.l2pf_a = l2pf > 0 ? l2pf : 0;
+        g.l2pf_b = (l2pf > 0 && linear_epi) ? l2pf : 0;
+        if (dual) g.l2pf_a = g.l2pf_b = 0;
+    }
     static const int exp_flags = env_int("MC_GEMM_EXP", 3);   // both measured wins (profiles/r2_first_experiments.txt); 0 = round-1 paths
     g.exp_flags = exp_flags;
     // bytes of B landing in ONE CTA's stage: the whole tile (single / multicast) or its half (pair mode)

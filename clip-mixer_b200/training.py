@@ -150,11 +150,20 @@ class FusedTrainStep:
         fork2 = torch.cuda.Event()
         fork2.record(main)
         side.wait_event(fork2)
-        self._tower_sms(1)
-        with torch.cuda.stream(side):
-            txt_t.backward(ws_t, b["dut"], prec, after_block=hook_t)                # accelerator.backward   :170
-        self._tower_sms(0)
-        img_t.backward(ws_i, b["dui"], prec, after_block=hook_i)
+        # The two backward passes are ENQUEUED block by block in alternation (text on the side stream, image on the main
+        # stream): the kernels still run concurrently, and the gradient buckets reach the single in-order communication
+        # stream in the order in which they become ready (see TowerRT.backward_iter).
+        gen_t = txt_t.backward_iter(ws_t, b["dut"], prec, after_block=hook_t)     # accelerator.backward   :170
+        gen_i = img_t.backward_iter(ws_i, b["dui"], prec, after_block=hook_i)
+        live_t = live_i = True
+        while live_t or live_i:
+            if live_t:
+                self._tower_sms(1)
+                with torch.cuda.stream(side):
+                    live_t = next(gen_t, None) is not None
+            if live_i:
+                self._tower_sms(0)
+                live_i = next(gen_i, None) is not None
         ops.set_sm_limit(0)
         main.wait_stream(side)
         self._finish_step()
