@@ -27,3 +27,4 @@ def test_two_ranks_equal_global_batch_oracle(precision):
     assert abs(r["loss"] - r["oracle_loss"]) <= tol * abs(r["oracle_loss"]), r
     assert not r["failed"], r
     assert r["buckets"] >= 3
+    assert r["replicas_bit_identical_after_4_steps"], r

@@ -40,13 +40,24 @@ def main():
     grads = {k: p.grad.detach().clone().cpu() for k, p in model.named_parameters()}
     loss_all = loss.clone()
     dist.all_reduce(loss_all)
+    # replicas must stay bit-identical: every rank holds the same all-reduced gradients, and the global grad norm (clip
+    # coefficient) is reduced in a fixed order (atomics made it rank-dependent)
+    for _ in range(3):
+        step.step(image[sl].to(dev), text[sl].to(dev))
+    torch.cuda.synchronize()
+    flat = model._require_store().flat_p
+    chk = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat[::9973].double().sum()])
+    allchk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    replicas_identical = all(torch.equal(allchk[0], c) for c in allchk)
     if rank == 0:
         truth = O.loss_and_grads({k: v.double() for k, v in sd.items()}, image.double(), text, world=world)
         tol = 1e-5 if precision == "fp32" else 2e-2
         worst, fails = O.compare_grads(grads, truth["grads"], tol)
         print(json.dumps({"world": world, "precision": precision, "loss": float(loss_all) / world,
                           "oracle_loss": float(truth["loss"]), "worst_grad_err": worst,
-                          "failed": [f[0] for f in fails], "buckets": len(dp.reducer.buckets)}), flush=True)
+                          "failed": [f[0] for f in fails], "buckets": len(dp.reducer.buckets),
+                          "replicas_bit_identical_after_4_steps": replicas_identical}), flush=True)
     torch.cuda.synchronize()
     dist.barrier()
     sys.stdout.flush()
