@@ -100,7 +100,10 @@ class ZeroShotScorer:
             else:
                 self._text_chunk(st, so)
             Wt[c0:c1].copy_(so[:c1 - c0])
-        self.W = Wt.t().contiguous()                                          # :133  [E, classes]
+        if self.W is not None and tuple(self.W.shape) == (self.E, C):
+            self.W.copy_(Wt.t())                                              # same buffer: the image-side graph stays valid
+        else:
+            self.W = Wt.t().contiguous()                                      # :133  [E, classes]
         return self.W
 
     def _image_batch(self, images, logits):
