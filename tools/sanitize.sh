@@ -12,7 +12,7 @@ SEL_T="tests/test_tokenmix_gpu.py -k '4-5-128 or 2-64-256 or 2-77-512'"
 for tool in memcheck synccheck racecheck; do
   for sel in "$SEL_G" "$SEL_T"; do
     echo "== compute-sanitizer --tool $tool : pytest $sel" >> $L
-    eval timeout 420 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 python -m pytest $sel -x -q -p no:cacheprovider 2>&1 \
+    eval timeout 240 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 python -m pytest $sel -x -q -p no:cacheprovider 2>&1 \
       | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error|Race|hazard|Barrier|Invalid|=========     at " | head -40 >> $L
   done
 done
