@@ -153,3 +153,32 @@ def test_trainer_resumes_from_accelerate_layout_checkpoint(tmp_path, monkeypatch
     assert len(got) == 6
     for a, b in zip(got, ref):
         assert abs(a - b) <= 1e-4 * abs(b), (got, ref)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_input_pipeline_delivers_batches_in_order(pinned):
+    """training.py:60-62,149,154 (DataLoader(pin_memory) + .to(device)) as the double-buffered InputPipeline: slots are
+    reused across many batches, pageable and pinned host sources, prefetch of batch k+1 issued before batch k is used."""
+    from clip_mixer_b200.training import InputPipeline
+    pipe = InputPipeline(torch.device(DEV))
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for i in range(7):
+        im = torch.randint(0, 256, (5, 3, 32, 32), dtype=torch.uint8, generator=g)
+        tx = torch.randint(0, 1000, (5, 12), generator=g)
+        if pinned:
+            im, tx = im.pin_memory(), tx.pin_memory()
+        batches.append((im, tx))
+    got = []
+    pipe.prefetch(*batches[0])
+    for i in range(len(batches)):
+        d_im, d_tx = pipe.next()
+        if i + 1 < len(batches):
+            pipe.prefetch(*batches[i + 1])
+        got.append((d_im.clone(), d_tx.clone()))          # "the step": reads the device slot on the compute stream
+        torch.cuda._sleep(int(2e6))                       # keep the compute stream busy while the next copy runs
+        pipe.release()
+    torch.cuda.synchronize()
+    for (im, tx), (d_im, d_tx) in zip(batches, got):
+        assert torch.equal(d_im.cpu(), im) and torch.equal(d_tx.cpu(), tx)
+    assert pipe.h2d_bytes == 5 * 3 * 32 * 32 + 5 * 12 * 8
