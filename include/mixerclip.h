@@ -233,7 +233,11 @@ int mc_l2norm_bwd(const float* du, const float* u, const float* inv_norm, float*
  *   log_scale  device scalar t (logit_scale parameter); labels g_i = rank*n + i
  * Outputs (fp32): loss[1] (+=, pre-zeroed by the caller), dui, dut [n, E] (overwritten),
  *   dlog_scale[1] (+=), all already divided for the mean over n and the /2.
- * workspace: mc_head_workspace_bytes(n, N, E) bytes.
+ * workspace: mc_head_workspace_bytes(n, N, E) bytes, 256-byte aligned.
+ * Two implementations behind the same entry point (MC_HEAD_TC = auto | 0 | 1): fp32 FFMA kernels (online softmax over
+ * 32-column tiles) for per-GPU batches, and from 2^24 logits per direction a tensor-core path: both contractions as
+ * bf16 x 3 split GEMMs on the tcgen05 engine (fp32-class accuracy), online softmax per 4096-column slab - one
+ * [n x 4096] fp32 slab of logits exists at a time, never the [n x N] matrix (n = 4096, N = 32768: 2.6 ms vs 57.6 ms).
  * ------------------------------------------------------------------------------------------ */
 int64_t mc_head_workspace_bytes(int64_t n, int64_t N, int64_t E);
 int mc_head_fwd_bwd(const float* ui, const float* ut, const float* ui_all, const float* ut_all, const float* log_scale,
