@@ -10,7 +10,7 @@ done
 MC_DP_TRACE=1 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout 240 $TR --master-port 29552 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_8gpu.json 2> gpurun_out/r2_bench_8gpu.err
 grep -m5 -i "nvls\|algo\|Using network\|channels" gpurun_out/r2_bench_8gpu.err | cut -c1-200 > gpurun_out/r2_nccl_info.txt
 MC_DP_BF16=1 timeout 200 $TR --master-port 29553 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_8gpu_bf16wire.json 2> /dev/null
-MC_HEAD_TC=0 timeout 300 $TR --master-port 29554 bench.py --gpus 8 --config 3 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_8gpu_config3.json 2> gpurun_out/r2_bench_8gpu_config3.err
+MC_SM_SPLIT=off timeout 300 $TR --master-port 29554 bench.py --gpus 8 --config 3 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_8gpu_config3.json 2> gpurun_out/r2_bench_8gpu_config3.err
 cat gpurun_out/r2_dp_check8.jsonl; for f in gpurun_out/r2_bench_8gpu.json gpurun_out/r2_bench_8gpu_bf16wire.json gpurun_out/r2_bench_8gpu_config3.json; do python - "$f" <<'PY'
 import json,sys
 try:

@@ -1,19 +1,26 @@
 #!/bin/bash
 # compute-sanitizer over the warp-specialised mbarrier kernels on reduced shapes (VERDICT r1 missing #8).
-# memcheck + synccheck + racecheck, each on a handful of small GEMM-engine and fused token-mixing tests; racecheck only
-# tracks shared-memory hazards between threads of the generic proxy (TMA / tcgen05 async-proxy accesses are ordered by
-# mbarriers it does not model), so its report is kept verbatim and read, not gated on.  Log: gpurun_out/r2_sanitizer.txt
+# memcheck + synccheck on a handful of small GEMM-engine and fused token-mixing tests, racecheck on the GEMM selection.
+# racecheck only tracks shared-memory hazards between threads of the generic proxy (TMA / tcgen05 async-proxy accesses are
+# ordered by mbarriers it does not model), so its report is kept verbatim and read, not gated on.
+# Log: gpurun_out/r2_sanitizer.txt
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 L=gpurun_out/r2_sanitizer.txt
 : > $L
-SEL_G="tests/test_gemm_gpu.py -k 'tc and (tn_aligned or ragged or lin3_like or lin4_like or dgrad_gelu_bwd or wgrad_splitk or tiny_dims)'"
-SEL_T="tests/test_tokenmix_gpu.py -k '4-5-128 or 2-64-256 or 2-77-512'"
-for tool in memcheck synccheck racecheck; do
-  for sel in "$SEL_G" "$SEL_T"; do
-    echo "== compute-sanitizer --tool $tool : pytest $sel" >> $L
-    eval timeout 240 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 python -m pytest $sel -x -q -p no:cacheprovider 2>&1 \
-      | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error|Race|hazard|Barrier|Invalid|=========     at " | head -40 >> $L
-  done
-done
+CS=/usr/local/cuda/bin/compute-sanitizer
+run() {   # run <tool> <file> <k-expression>
+  echo "== compute-sanitizer --tool $1 : pytest $2 -k \"$3\"" >> $L
+  timeout 150 $CS --tool $1 --print-limit 10 --error-exitcode 0 python -m pytest $2 -k "$3" -x -q -p no:cacheprovider > /tmp/san.out 2>&1
+  echo "   exit $? ($(wc -l < /tmp/san.out) lines of output)" >> $L
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|rror|hazard|Invalid|Barrier|=========     at " /tmp/san.out | head -25 >> $L
+  tail -4 /tmp/san.out | cut -c1-200 >> $L
+}
+G="tc and (tn_aligned or ragged or lin3_like or lin4_like or dgrad_gelu_bwd or wgrad_splitk or tiny_dims)"
+T="4-5-128 or 2-64-256 or 2-77-512"
+run memcheck tests/test_gemm_gpu.py "$G"
+run memcheck tests/test_tokenmix_gpu.py "$T"
+run synccheck tests/test_gemm_gpu.py "$G"
+run synccheck tests/test_tokenmix_gpu.py "$T"
+run racecheck tests/test_gemm_gpu.py "tc and (tn_aligned or lin4_like or dgrad_gelu_bwd)"
 cat $L
