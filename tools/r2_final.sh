@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, final single-GPU check: smoke(), the whole GPU suite, the default bench line, sanitizer
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.txt 2>&1; tail -2 gpurun_out/r2_final_smoke.txt
+timeout 900 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^$" | grep -E "^\[|passed|failed|FAILED|Error|EXEMPT|skipped|losses" | cut -c1-400 > gpurun_out/r2_final_gpu_tests.log; tail -3 gpurun_out/r2_final_gpu_tests.log
+timeout 400 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; tail -c 700 gpurun_out/r2_final_bench.json
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/r2_final_bench_reference.json
+bash tools/sanitize.sh > /dev/null 2>&1; tail -30 gpurun_out/r2_sanitizer.txt
