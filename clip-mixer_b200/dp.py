@@ -146,7 +146,10 @@ class DataParallel:
     feature gather.  ``isinstance(x, DataParallel)`` plays the role of the reference's
     ``isinstance(self.model, DistributedDataParallel)`` branch (training.py:174)."""
 
-    def __init__(self, model, group=None, min_bucket_mb: float = 8.0):
+    def __init__(self, model, group=None, min_bucket_mb: float = None):
+        import os
+        if min_bucket_mb is None:
+            min_bucket_mb = float(os.environ.get("MC_DP_BUCKET_MB", "8"))     # smallest all-reduce message (blocks are merged up to it)
         self.module, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
