@@ -452,8 +452,12 @@ class Trainer:
     """Shape of the reference's Trainer (training.py:30-250) over FusedTrainStep and synthetic data."""
 
     def __init__(self, model, preprocess=None, epochs: int = 1, args=None, batch_size: int = 256,
-                 steps_per_epoch: int = 10, use_cuda_graph: bool = False):
+                 steps_per_epoch: int = 10, use_cuda_graph: bool = False, validators=None):
         self.epochs = epochs
+        # the reference builds ImageNet / STS / MNIST / SST-2 validators here (training.py:98-104); their datasets are out of
+        # scope, so the caller passes objects with the same ``validate(step, verbose)`` method (zeroshot.ZeroShotValidator)
+        self.validators = list(validators) if validators is not None else []
+        self.validation_results = []
         self.model = model
         self.preprocess = preprocess
         self.runName = getattr(args, "run_name", "run") if args is not None else "run"
@@ -508,9 +512,12 @@ class Trainer:
         return [float(l) for l in self.losses]
 
     def validate(self, step):
-        """The reference runs ImageNetV2 / STS / MNIST / SST-2 validators here (training.py:211-216); they
-        need datasets that are not reachable offline.  The zero-shot scoring shape is in zeroshot.py."""
-        return None
+        """training.py:211-216: every validator runs on the local main process."""
+        out = None
+        if self.rank == 0:
+            out = [v.validate(step, True) for v in self.validators]
+            self.validation_results.append((step, out))
+        return out
 
     def save_model(self, currentEpoch: int, currentStep: int = 0, savePath: Optional[str] = None):
         """training.py:218-229: ``accelerator.save_state(path)`` + ``epoch.json`` + barrier (the Azure mirror is out of

@@ -145,6 +145,42 @@ class ZeroShotScorer:
         return so
 
 
+class ZeroShotValidator:
+    """Shape of the reference's ``ImageNetValidator`` (validation.py:114-181) over ZeroShotScorer: built with the class
+    prompts (token ids ``[classes, templates, context]``; the reference tokenises 1000 names x 80 templates, :119-124) and
+    a loader of ``(images, target)`` batches, ``validate(step, verbose)`` switches the model to eval, rebuilds the
+    classifier from the current weights (:149), scores every batch (``100 * f @ W``, :157-162) and returns / logs top-1 and
+    top-5 accuracy in percent (:164-179).  The datasets themselves (ImageNetV2, ...) are out of scope: the caller
+    brings the loader."""
+
+    def __init__(self, trainer, class_tokens: torch.Tensor, loader, writer=None, classes_per_chunk: int = 50,
+                 use_cuda_graph: bool = True):
+        self.trainer, self.class_tokens, self.loader, self.writer = trainer, class_tokens, loader, writer
+        self.scorer = ZeroShotScorer(trainer.model, class_tokens.shape[1], classes_per_chunk, use_cuda_graph)
+
+    @torch.no_grad()
+    def validate(self, step, verbose=False):
+        model = self.trainer.model
+        was_training = model.training
+        model.eval()                                                          # :143-146
+        dev = model.logit_scale.device
+        self.scorer.build_classifier(self.class_tokens.to(dev))               # :149
+        top1 = top5 = n = 0.0
+        for images, target in self.loader:                                    # :153-168
+            logits = self.scorer.logits(images.to(dev))
+            a1, a5 = accuracy(logits, target.to(dev), topk=(1, 5))
+            top1, top5, n = top1 + a1, top5 + a5, n + images.shape[0]
+        top1, top5 = top1 / max(n, 1) * 100, top5 / max(n, 1) * 100           # :170-171
+        if verbose:
+            print(f"Top-1 accuracy: {top1:.2f}%")
+            print(f"Top-5 accuracy: {top5:.2f}%")
+        if self.writer is not None:
+            self.writer.add_scalar("Top-1 accuracy", top1, step)
+            self.writer.add_scalar("Top-5 accuracy", top5, step)
+        model.train(was_training)
+        return {"top1": top1, "top5": top5, "n": int(n)}
+
+
 def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)):
     """validation.py:136-139."""
     pred = output.topk(max(topk), 1, True, True)[1].t()

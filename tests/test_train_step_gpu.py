@@ -182,3 +182,32 @@ def test_input_pipeline_delivers_batches_in_order(pinned):
     for (im, tx), (d_im, d_tx) in zip(batches, got):
         assert torch.equal(d_im.cpu(), im) and torch.equal(d_tx.cpu(), tx)
     assert pipe.h2d_bytes == 5 * 3 * 32 * 32 + 5 * 12 * 8
+
+
+def test_trainer_runs_its_validators_like_the_reference(tmp_path, monkeypatch):
+    """training.py:98-104,205,211-216 + validation.py:142-179: Trainer.validate() drives validator objects; the zero-shot
+    validator rebuilds the classifier from the CURRENT weights, scores a loader of (images, target) and reports top-1 /
+    top-5 in percent.  Targets are the oracle's own predictions, so both accuracies must be 100 %."""
+    from clip_mixer_b200.training import Trainer
+    from clip_mixer_b200.zeroshot import ZeroShotValidator
+    from oracle import mixer_clip_oracle as O
+    monkeypatch.chdir(tmp_path)
+    cfg = O.CONFIGS["tiny"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    model = _model(cfg, sd, "fp32")
+    classes, templates = 6, 3
+    prompts = torch.stack([O.synthetic_batch(cfg, templates, seed=200 + c)[1] for c in range(classes)])
+    images, _ = O.synthetic_batch(cfg, 10, seed=77)
+    cols = []
+    for c in range(classes):
+        e = O.encode_text(sd, prompts[c])
+        e = (e / e.norm(dim=-1, keepdim=True)).mean(0)
+        cols.append(e / e.norm())
+    f = O.encode_image(sd, images)
+    target = ((f / f.norm(dim=-1, keepdim=True)) @ torch.stack(cols, 1)).argmax(1)
+    trainer = Trainer(model, batch_size=8, steps_per_epoch=0, epochs=1)
+    trainer.validators = [ZeroShotValidator(trainer, prompts, [(images[:6], target[:6]), (images[6:], target[6:])],
+                                            classes_per_chunk=4)]
+    out = trainer.validate(0)
+    assert out[0]["n"] == 10 and out[0]["top1"] == 100.0 and out[0]["top5"] == 100.0
+    assert model.training
