@@ -205,7 +205,7 @@ def test_trainer_runs_its_validators_like_the_reference(tmp_path, monkeypatch):
         cols.append(e / e.norm())
     f = O.encode_image(sd, images)
     target = ((f / f.norm(dim=-1, keepdim=True)) @ torch.stack(cols, 1)).argmax(1)
-    trainer = Trainer(model, batch_size=8, steps_per_epoch=0, epochs=1)
+    trainer = Trainer(model, batch_size=8, steps_per_epoch=3, epochs=1)
     trainer.validators = [ZeroShotValidator(trainer, prompts, [(images[:6], target[:6]), (images[6:], target[6:])],
                                             classes_per_chunk=4)]
     out = trainer.validate(0)
