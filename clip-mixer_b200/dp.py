@@ -149,7 +149,10 @@ class DataParallel:
     def __init__(self, model, group=None, min_bucket_mb: float = None):
         import os
         if min_bucket_mb is None:
-            min_bucket_mb = float(os.environ.get("MC_DP_BUCKET_MB", "8"))     # smallest all-reduce message (blocks are merged up to it)
+            # smallest all-reduce message (blocks are merged up to it).  Measured on 8 B200s (profiles/r2d_bench_8gpu_bucket*):
+            # 8 MB = 27 latency-bound messages, 4.2 ms of all-reduce kernels competing with the persistent GEMMs, 16.31 ms per
+            # step; 64-256 MB = 3-7 messages, 1.5-2.2 ms, 15.75-15.84 ms; 64 MB keeps the exposed tail smallest (0.68 ms)
+            min_bucket_mb = float(os.environ.get("MC_DP_BUCKET_MB", "64"))
         self.module, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
