@@ -76,6 +76,9 @@ struct TmArgs {
     int zpitch;               // TMEM columns between Z and dH inside a working buffer (>= widest segment, multiple of 32)
     int ybufs;                // output tiles in TMEM (2 forward, 1 dgrad)
     int stages;
+    int stagger;              // FWD, two Z buffers: E1 groups {0,1} own the segments of buffer 0, groups {2,3} those of buffer 1 (two
+                              // chunks per warp and segment), so the two pairs are in different phases instead of all 16 warps
+                              // waiting, computing and storing in lock-step
     int aug;                  // 1: lin1's bias rides in the up GEMM (needs two spare k-rows, Ppad - P >= 2): U rows P, P+1 are
                               // constant ones, W1^T rows P, P+1 hold the bf16 hi / lo parts of b1 - the E1 warps add nothing
     uint32_t u_tx_bytes;      // bytes one TMA load of a U group delivers (aug: P rows, else Ppad rows)
@@ -220,7 +223,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&z_full[s]), 1);
-            mbar_init(smem_u32(&z_empty[s]), kE1Warps);
+            mbar_init(smem_u32(&z_empty[s]), g.stagger ? kE1Warps / 2 : kE1Warps);
             mbar_init(smem_u32(&y_full[s]), 1);
             mbar_init(smem_u32(&y_empty[s]), kE2Warps);
         }
@@ -488,6 +491,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
             for (int s = 0; s < nseg; ++s, ++sc) {
                 const uint32_t b = nbuf == 2 ? (sc & 1u) : 0u;
+                if (g.stagger && b != (uint32_t)(grp >> 1)) continue;      // the other pair of groups owns this segment
                 TM_TR(warp, 1);
                 mbar_wait_relaxed(smem_u32(&z_full[b]), nbuf == 2 ? ((sc >> 1) & 1u) : (sc & 1u), 20);
                 TM_TR(warp, 2);
@@ -500,7 +504,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 mbar_wait_relaxed(smem_u32(&h_empty[s]), (n & 1u) ^ 1u, 20);
                 TM_TR(warp, 3);
                 for (int c = 2 * a0; c < 2 * a1; ++c) {
-                    if (c % kE1Groups != grp) continue;
+                    if (g.stagger ? (c & 1) != (grp & 1) : c % kE1Groups != grp) continue;
                     const int a = c >> 1, par = c & 1;
                     const int col = c * 32;                  // tile-local hidden column of this warp's chunk
                     const int rel = col - s * SW;
@@ -780,6 +784,10 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         const char* na = getenv("MC_TM_NO_AUG");       // A/B knob: bias added by the E1 warps as in round 1
         g.aug = (g.Ppad - g.P >= 2 && !(na != nullptr && atoi(na) != 0)) ? 1 : 0;
     }
+    {
+        const char* sg = getenv("MC_TM_STAGGER");
+        g.stagger = (mode == TM_FWD && sg != nullptr && atoi(sg) != 0) ? 1 : 0;      // needs nbuf == 2 (checked below)
+    }
     const int u_rows = g.aug ? g.P : g.Ppad;
     g.u_tx_bytes = (uint32_t)u_rows * 128u;
     g.w1 = reinterpret_cast<const __nv_bfloat16*>(p->w1); g.ld1 = (int)p->ld1;
@@ -835,6 +843,7 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         }
     }
     MC_CHECK(g.SW >= 64 && g.SW <= 256, "token_mix: bad segment width");
+    if (g.nbuf != 2) g.stagger = 0;
     if (mode == TM_WGRAD) {
         g.nslices = (g.Hpad + g.slice_w - 1) / g.slice_w;
         natoms_smem = g.slice_w / 64;
