@@ -76,6 +76,8 @@ struct TmArgs {
     int zpitch;               // TMEM columns between Z and dH inside a working buffer (>= widest segment, multiple of 32)
     int ybufs;                // output tiles in TMEM (2 forward, 1 dgrad)
     int stages;
+    int early;                // FWD: an E1 warp hands the Z buffer back as soon as its last chunk of the segment is in registers (before
+                              // the QuickGELU / store work), so the up GEMMs of the segment after next start ~1 k clocks earlier
     int stagger;              // FWD, two Z buffers: E1 groups {0,1} own the segments of buffer 0, groups {2,3} those of buffer 1 (two
                               // chunks per warp and segment), so the two pairs are in different phases instead of all 16 warps
                               // waiting, computing and storing in lock-step
@@ -503,6 +505,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 // the down GEMMs of the previous tile have released this segment's operand atoms
                 mbar_wait_relaxed(smem_u32(&h_empty[s]), (n & 1u) ^ 1u, 20);
                 TM_TR(warp, 3);
+                bool released = false;
                 for (int c = 2 * a0; c < 2 * a1; ++c) {
                     if (g.stagger ? (c & 1) != (grp & 1) : c % kE1Groups != grp) continue;
                     const int a = c >> 1, par = c & 1;
@@ -515,8 +518,22 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                             // turned into bf16 (the MUFU-bound part), so only one load latency per chunk is exposed
                             uint32_t va[16], vb[16];
                             tmem_ld16(zcol + rel, va);
-                            tmem_ld_wait();
-                            tmem_ld16(zcol + rel + 16, vb);
+                            if (g.early) {
+                                // both halves requested at once; when they have arrived and this is the warp's last chunk of
+                                // the segment, the Z buffer goes back to the up-GEMM issuer before any math is done on it
+                                tmem_ld16(zcol + rel + 16, vb);
+                                tmem_ld_wait();
+                                const int cstep = g.stagger ? 2 : kE1Groups;
+                                if (c + cstep >= 2 * a1 || (c + cstep) * 32 >= my_hpad) {
+                                    tc_fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive(smem_u32(&z_empty[b]));
+                                    released = true;
+                                }
+                            } else {
+                                tmem_ld_wait();
+                                tmem_ld16(zcol + rel + 16, vb);
+                            }
                             auto half = [&](const uint32_t (&v)[16], int hf) {
                                 uint32_t o[8];
                                 if (g.aug) {        // the accumulator already holds W1 u + b1
@@ -539,7 +556,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                                 tm_sts128(dst + (((cc + 1) ^ sw) << 4), o[4], o[5], o[6], o[7]);
                             };
                             half(va, 0);
-                            tmem_ld_wait();
+                            if (!g.early) tmem_ld_wait();
                             half(vb, 1);
                         } else {
                             const uint32_t dst2 = h2buf + a * kAtomBytes + row_off;
@@ -584,7 +601,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 TM_TR(warp, 4);
-                if (lane == 0) mbar_arrive(smem_u32(&z_empty[b]));
+                if (lane == 0 && !released) mbar_arrive(smem_u32(&z_empty[b]));
             }
         }
         if (MODE == TM_WGRAD) {
@@ -785,8 +802,12 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
         g.aug = (g.Ppad - g.P >= 2 && !(na != nullptr && atoi(na) != 0)) ? 1 : 0;
     }
     {
+        // both on by default since round 2 (profiles/r2g_tokenmix_stagger_early.txt: forward 37.0 / 36.9 -> 35.6 / 33.1 us for the
+        // image / text tower; early release alone is a loss, it needs the staggered groups); MC_TM_STAGGER=0 / MC_TM_EARLY=0 for A/B
         const char* sg = getenv("MC_TM_STAGGER");
-        g.stagger = (mode == TM_FWD && sg != nullptr && atoi(sg) != 0) ? 1 : 0;      // needs nbuf == 2 (checked below)
+        g.stagger = (mode == TM_FWD && !(sg != nullptr && atoi(sg) == 0)) ? 1 : 0;      // needs nbuf == 2 (checked below)
+        const char* er = getenv("MC_TM_EARLY");
+        g.early = (mode == TM_FWD && !(er != nullptr && atoi(er) == 0)) ? 1 : 0;
     }
     const int u_rows = g.aug ? g.P : g.Ppad;
     g.u_tx_bytes = (uint32_t)u_rows * 128u;
@@ -844,6 +865,7 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     }
     MC_CHECK(g.SW >= 64 && g.SW <= 256, "token_mix: bad segment width");
     if (g.nbuf != 2) g.stagger = 0;
+    if (!g.stagger) g.early = 0;
     if (mode == TM_WGRAD) {
         g.nslices = (g.Hpad + g.slice_w - 1) / g.slice_w;
         natoms_smem = g.slice_w / 64;
