@@ -38,6 +38,7 @@ class GemmParams(C.Structure):
         ("A2", C.c_void_p), ("a2_major", C.c_int32), ("lda2", C.c_int64), ("a2_batch_stride", C.c_int64),
         ("B2", C.c_void_p), ("b2_major", C.c_int32), ("ldb2", C.c_int64), ("b2_batch_stride", C.c_int64),
         ("bias2", C.c_void_p),
+        ("rowstat_out", C.c_void_p),
     ]
 
 
@@ -49,6 +50,8 @@ class TokenMixParams(C.Structure):
         ("w2", C.c_void_p), ("ld2", C.c_int64), ("b2", C.c_void_p),
         ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p),
         ("gw1", C.c_void_p), ("ldg1", C.c_int64), ("gw2", C.c_void_p), ("ldg2", C.c_int64), ("gb1", C.c_void_p),
+        ("ln_sums", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("u_out", C.c_void_p),
+        ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
     ]
 
 

@@ -118,6 +118,7 @@ extern "C" int mc_gemm_f32_simt(const mc_gemm_params* p, void* stream_) {
     MC_CHECK(p->A && p->B && p->C, "gemm: null operand");
     MC_CHECK(p->c_dtype == MC_F32, "simt gemm writes fp32 only");
     MC_CHECK(p->A2 == nullptr && p->B2 == nullptr, "simt gemm: the recompute operand pair (A2/B2) is a tensor-core engine feature");
+    MC_CHECK(p->rowstat_out == nullptr, "simt gemm: rowstat_out is a tensor-core engine feature");
     MC_CHECK(p->act != MC_ACT_GELU_BWD || p->zin != nullptr, "gemm: GELU_BWD needs zin");
     MC_CHECK(p->bias_mode == MC_BIAS_NONE || p->bias != nullptr, "gemm: bias_mode set without bias");
     SimtArgs g{};

@@ -84,6 +84,7 @@ struct GemmTcArgs {
     const float* R;
     long long ldr, r_bs;
     float* rowsum_out;   // optional: rowsum_out[m] += sum over (batch, n) of the stored value
+    float* rowstat_out;  // optional (residual epilogue): rowstat_out[2m] += sum_n x, [2m+1] += sum_n x^2 of the stored value
     int c_transposed;    // C / R element (m, n) at n*ld + m
     // second operand pair (recompute of the pre-activation): acc2 lands 128 TMEM columns after acc
     int dual, a2_mn, b2_mn, a2_batched, b2_batched, pair_bytes;
@@ -663,6 +664,7 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
         tmem_ld_wait();
         if (!row_ok) return;
         float* cp = reinterpret_cast<float*>(g.C) + (long long)b * g.c_bs + crow * g.ldc + n;
+        float st1 = 0.f, st2 = 0.f;      // row statistics of the stored values (rowstat_out)
         if (full && g.vec_ok) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -677,15 +679,29 @@ __device__ __forceinline__ void chunk32_staged(const GemmTcArgs& g, const CUtens
                     for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]) + bias_m + __uint_as_float(r[8 * j + i]);
                 }
                 stg256f(cp + 8 * j, o);
+                if (g.rowstat_out != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        st1 += o[i];
+                        st2 = fmaf(o[i], o[i], st2);
+                    }
+                }
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 if (n + i < g.N) {
                     const float bb = g.bias_mode == MC_BIAS_N ? g.bias[n + i] : bias_m;
-                    cp[i] = __uint_as_float(v[i]) + bb + __uint_as_float(r[i]);
+                    const float o = __uint_as_float(v[i]) + bb + __uint_as_float(r[i]);
+                    cp[i] = o;
+                    st1 += o;
+                    st2 = fmaf(o, o, st2);
                 }
             }
+        }
+        if (g.rowstat_out != nullptr) {
+            atomicAdd(g.rowstat_out + 2 * crow, st1);
+            atomicAdd(g.rowstat_out + 2 * crow + 1, st2);
         }
     } else {  // EPI_PLAIN: fp32 tile, plain store or reduce-add (accumulate / split-K)
         tmem_ld32(taddr, v);
@@ -1562,6 +1578,9 @@ extern "C" int mc_gemm_bf16_tc(const mc_gemm_params* p, void* stream_) {
     g.zin = reinterpret_cast<const __half*>(p->zin); g.ldzin = p->ldzin; g.zin_bs = p->zin_batch_stride;
     g.act = p->act; g.R = p->R; g.ldr = p->ldr; g.r_bs = p->r_batch_stride;
     g.rowsum_out = p->rowsum_out;
+    g.rowstat_out = p->rowstat_out;
+    MC_CHECK(p->rowstat_out == nullptr || (epi == EPI_RESID && g.tma_epi && g.out_batch == 1 && p->row_remap == 0 && !p->c_transposed),
+             "gemm: rowstat_out needs the TMA residual epilogue (act NONE, fp32 C, aligned R), batch 1, no row_remap");
     g.c_transposed = p->c_transposed ? 1 : 0;
     MC_CHECK(p->rowsum_out == nullptr || epi == EPI_ACT_BWD || epi == EPI_ACT_BWD_DUAL || epi == EPI_GENERIC,
              "gemm: rowsum_out is supported with the GELU-backward and generic epilogues only");

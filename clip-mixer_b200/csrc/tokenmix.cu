@@ -76,6 +76,15 @@ struct TmArgs {
     int zpitch;               // TMEM columns between Z and dH inside a working buffer (>= widest segment, multiple of 32)
     int ybufs;                // output tiles in TMEM (2 forward, 1 dgrad)
     int stages;
+    // FWD with LayerNorm in the prologue (ln_sums != nullptr): the E2 warps read the fp32 block input themselves, normalise it
+    // with the row statistics the producing GEMM left behind (sum, sum of squares per token row) and write the bf16 operand
+    // tile straight into the swizzled smem stage (and to u_out for the backward kernels); no TMA load of u, no LayerNorm kernel
+    const float* ln_sums;     // [B*P][2]
+    const float* ln_gamma;
+    const float* ln_beta;
+    __nv_bfloat16* u_out;     // [B, P, D]
+    float* ln_mean;           // [B*P] out (LayerNorm backward reads them)
+    float* ln_rstd;
     int early;                // FWD: an E1 warp hands the Z buffer back as soon as its last chunk of the segment is in registers (before
                               // the QuickGELU / store work), so the up GEMMs of the segment after next start ~1 k clocks earlier
     int stagger;              // FWD, two Z buffers: E1 groups {0,1} own the segments of buffer 0, groups {2,3} those of buffer 1 (two
@@ -178,6 +187,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __shared__ __align__(8) uint64_t y_empty[2];
     __shared__ __align__(8) uint64_t w_full;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float2 lnstat[kMaxTmStages][96];       // (mean, rstd) of the tokens of the tile in each stage (fused LayerNorm)
 
 #ifndef MC_DIVERGENT_WARP_IDX
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index (see gemm_tc.cu)
@@ -219,8 +229,9 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     }
     if (warp == kInitWarp && lane == 0) {
         mbar_init(smem_u32(&w_full), 1);
+        const bool fuse_ln_init = MODE == TM_FWD && g.ln_sums != nullptr;
         for (int s = 0; s < kMaxTmStages; ++s) {
-            mbar_init(smem_u32(&u_full[s]), 1);
+            mbar_init(smem_u32(&u_full[s]), fuse_ln_init ? kE2Warps : 1);   // fused LayerNorm: the E2 warps fill the stage
             mbar_init(smem_u32(&u_empty[s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -270,6 +281,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d0 + 32 * i, 0, b);
         }
     };
+    const bool fuse_ln = MODE == TM_FWD && g.ln_sums != nullptr;
     int npre = 0;      // tiles requested in the prologue (one per smem stage)
     if (warp == kProdWarp) {
         if (lane == 0) {
@@ -281,8 +293,10 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 tma_load_3d(w2t + (uint32_t)a * g.grp_bytes, &tmW2, wb, jbase + 64 * a, 0, 0);
             }
         }
-        for (int t = work0; t < g.num_tiles && npre < g.stages; t += work_stride, ++npre)
-            if (lane == 0) issue_tile(t, (uint32_t)npre);
+        if (!fuse_ln) {
+            for (int t = work0; t < g.num_tiles && npre < g.stages; t += work_stride, ++npre)
+                if (lane == 0) issue_tile(t, (uint32_t)npre);
+        }
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -290,12 +304,12 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
         if (i < g.natoms * 64) b1s[i] = b1v[it];
     }
     if (MODE == TM_FWD && (int)threadIdx.x < g.Ppad) b2s[threadIdx.x] = b2v;
-    if (MODE == TM_WGRAD || g.aug) {
+    if (MODE == TM_WGRAD || g.aug || fuse_ln) {
         // Constant rows of every U group, written once (TMA only rewrites the rows of its box: P rows with aug, else Ppad):
         //   aug:   rows P and P+1 are all ones - with W1^T rows P / P+1 = hi / lo halves of b1 the up GEMM adds the bias;
         //   WGRAD: row Ppad is all ones (its accumulator lane collects db1 = sum_d dZ1); every other row >= P is zero.
         const uint32_t stage0 = base + g.off_stage;
-        const int r_lo = g.aug ? g.P : g.Ppad, r_hi = MODE == TM_WGRAD ? 128 : g.Ppad;
+        const int r_lo = (g.aug || fuse_ln) ? g.P : g.Ppad, r_hi = MODE == TM_WGRAD ? 128 : g.Ppad;   // fused LN: nobody else writes rows >= P
         const int rows_c = r_hi - r_lo;
         for (int s = 0; s < g.stages; ++s)
             for (int grp = 0; grp < 2; ++grp)
@@ -340,7 +354,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 
     if (warp == kProdWarp) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (lane == 0 && !fuse_ln) {
             uint32_t st = 0, ph = 0;
             int it = 0;
             for (int t = work0; t < g.num_tiles; t += work_stride, ++it) {
@@ -638,7 +652,68 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             const int nch = g.Ppad / 16;
             const int Dd = TD ? TD : g.D;
             uint32_t n = 0;
+            // ---- LayerNorm in the prologue (model.py:216 folded into :220-222): this warp group produces the bf16 operand
+            //      tile of tile `tp` in stage j % stages from the fp32 block input and the row sums of the producing GEMM ----
+            auto produce = [&](int tp, uint32_t j) {
+                const uint32_t st_ = j % (uint32_t)g.stages, use = j / (uint32_t)g.stages;
+                const int b = tp / g.tiles_d, d0 = (tp - b * g.tiles_d) * 128;
+                const int dl = q * 32 + lane;                                  // channel inside the 128-wide slab
+                const long long gb = ((long long)b * g.P + hsel * 16) * Dd + d0 + dl;
+                if (use > 0) mbar_wait_relaxed(smem_u32(&u_empty[st_]), (use - 1u) & 1u, 32);   // the up GEMMs have read the old tile
+                float xv[3][16];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int p0 = hsel * 16 + 32 * k;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xv[k][i] = p0 + i < g.P ? __ldg(g.x + gb + (long long)(32 * k + i) * Dd) : 0.f;
+                }
+                const float gam = __ldg(g.ln_gamma + d0 + dl), bet = __ldg(g.ln_beta + d0 + dl);
+                if ((int)threadIdx.x < g.P) {
+                    const float2 sm = __ldg(reinterpret_cast<const float2*>(g.ln_sums) + (long long)b * g.P + threadIdx.x);
+                    const float invD = 1.0f / (float)Dd;
+                    const float mean = sm.x * invD;
+                    const float var = fmaxf(fmaf(-mean, mean, sm.y * invD), 0.f);
+                    const float rstd = rsqrtf(var + kLnEps);
+                    lnstat[st_][threadIdx.x] = make_float2(mean, rstd);
+                    if (d0 == 0) {                                               // one slab per sample writes the saved statistics
+                        g.ln_mean[(long long)b * g.P + threadIdx.x] = mean;
+                        g.ln_rstd[(long long)b * g.P + threadIdx.x] = rstd;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");                 // the eight E2 warps
+                const uint32_t srow = base + g.off_stage + st_ * g.stage_bytes + (uint32_t)(dl >> 6) * g.a_grp_bytes +
+                                      (uint32_t)(dl & 7) * 2u;
+                const uint32_t c8 = (uint32_t)((dl & 63) >> 3);
+                __nv_bfloat16* ug = g.u_out + gb;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = hsel * 16 + 32 * k + i;
+                        if (p < g.P) {
+                            const float2 ms = lnstat[st_][p];
+                            const __nv_bfloat16 uv = __float2bfloat16_rn(fmaf((xv[k][i] - ms.x) * ms.y, gam, bet));
+                            const unsigned short bits = *reinterpret_cast<const unsigned short*>(&uv);
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(srow + (uint32_t)p * 128u + ((c8 ^ ((uint32_t)p & 7u)) << 4)),
+                                         "h"(bits) : "memory");
+                            ug[(long long)(32 * k + i) * Dd] = uv;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&u_full[st_]));
+            };
+            if (fuse_ln && work0 < g.num_tiles) produce(work0, 0u);
             for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
+                if (fuse_ln) {
+                    if (t + work_stride < g.num_tiles) produce(t + work_stride, n + 1u);   // overlaps the E1 pass of tile t
+                    if (e2 == 0 && lane == 0 && t + 2 * work_stride < g.num_tiles) {        // pull the tile after next into L2
+                        const int t2 = t + 2 * work_stride, b2_ = t2 / g.tiles_d, d2 = (t2 - b2_ * g.tiles_d) * 128;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d2 + 32 * i, 0, b2_);
+                    }
+                }
                 const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
                 // this warp owns the 16-token chunks hsel, hsel + 2, hsel + 4: token p = hsel*16 + 32*k + i
                 const long long gbase = ((long long)b * g.P + hsel * 16) * Dd + d0 + q * 32 + lane;
@@ -784,7 +859,10 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     MC_CHECK(p->B > 0 && p->P > 0 && p->D > 0, "token_mix: empty problem");
     MC_CHECK(mc_token_mix_supported(p->P, p->D), "token_mix: unsupported shape P=%lld D=%lld (need P <= 80, D %% 128 == 0)",
              (long long)p->P, (long long)p->D);
-    MC_CHECK(p->u && p->w1 && p->w2 && p->b1, "token_mix: null operand");
+    const bool fuse_ln_h = mode == TM_FWD && p->ln_sums != nullptr;
+    MC_CHECK((p->u || fuse_ln_h) && p->w1 && p->w2 && p->b1, "token_mix: null operand");
+    MC_CHECK(!fuse_ln_h || (p->ln_gamma && p->ln_beta && p->u_out && p->ln_mean && p->ln_rstd && p->P <= 96),
+             "token_mix fwd with fused LayerNorm: ln_gamma, ln_beta, u_out, ln_mean, ln_rstd are required");
     MC_CHECK(p->w1t != nullptr && p->ld1t >= 4 * p->P && p->ld1t % 8 == 0 && (reinterpret_cast<uintptr_t>(p->w1t) & 15) == 0,
              "token_mix: w1t (W1^T bf16 [P x ld1t], mc_transpose_bf16 of w1; ld1t >= 4P, multiple of 8, 16-byte aligned) is required");
     TmArgs g{};
@@ -814,6 +892,9 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     g.w1 = reinterpret_cast<const __nv_bfloat16*>(p->w1); g.ld1 = (int)p->ld1;
     g.w2 = reinterpret_cast<const __nv_bfloat16*>(p->w2); g.ld2 = (int)p->ld2;
     g.b1 = p->b1; g.b2 = p->b2; g.x = p->x; g.y = p->y;
+    g.ln_sums = fuse_ln_h ? p->ln_sums : nullptr;
+    g.ln_gamma = p->ln_gamma; g.ln_beta = p->ln_beta; g.u_out = reinterpret_cast<__nv_bfloat16*>(p->u_out);
+    g.ln_mean = p->ln_mean; g.ln_rstd = p->ln_rstd;
     MC_CHECK(g.ld1 >= g.P && g.ld2 >= g.H && g.ld1 % 8 == 0 && g.ld2 % 8 == 0, "token_mix: weight pitches must be >= the row length and multiples of 8");
     MC_CHECK((reinterpret_cast<uintptr_t>(p->w1) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w2) & 15) == 0,
              "token_mix: weights must be 16-byte aligned");
@@ -940,7 +1021,7 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     rcw = tm_make_map(&tmW2, p->w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.H, g.P, 1, g.ld2, (int64_t)g.P * g.ld2, 64, g.Ppad,
                       CU_TENSOR_MAP_SWIZZLE_128B, "w2");
     if (rcw != MC_OK) return rcw;
-    int rc = tm_make_map(&tmU, p->u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.D, g.P, g.B, g.D, (int64_t)g.P * g.D, 64, u_rows,
+    int rc = tm_make_map(&tmU, fuse_ln_h ? p->u_out : p->u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.D, g.P, g.B, g.D, (int64_t)g.P * g.D, 64, u_rows,
                          CU_TENSOR_MAP_SWIZZLE_128B, "u");
     if (rc != MC_OK) return rc;
     if (mode != TM_FWD) {

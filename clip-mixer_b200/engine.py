@@ -23,6 +23,12 @@ from .ops import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, BIAS_M, BIAS_N, MAJOR_K, MAJ
 from .params import ParamStore
 
 
+def fused_ln_prologue_enabled() -> bool:
+    """MC_TM_FUSE_LN=0 keeps LayerNorm 1 of every block as its own kernel (A/B); default: blocks 1.. take it in the
+    prologue of the fused token-mixing forward kernel, with row statistics from the preceding lin4 GEMM's epilogue."""
+    return os.environ.get("MC_TM_FUSE_LN", "1") != "0"
+
+
 def fused_token_mix_enabled() -> bool:
     """MC_TOKENMIX=gemm selects the unfused token-mixing schedule (separate engine GEMMs with a materialised
     [B, 4P, D] hidden tensor) for A/B measurements; the default is the fused kernels of csrc/tokenmix.cu."""
@@ -65,6 +71,9 @@ class TowerWS:
         self.z2 = torch.empty(n, B * P, 4 * D, device=device, dtype=zdt) if save else None
         self.h2 = torch.empty(n, B * P, 4 * D, **a)
         self.stats = torch.empty(n, 4, B * P, **f32)                  # mean1, rstd1, mean2, rstd2
+        # fused LayerNorm prologue: (sum, sum of squares) over D of every row of a block's input, left behind by the lin4 GEMM
+        # that produced it (slot i = input of block i; slot 0 is unused: block 0's input comes from ln_pre / the embedding)
+        self.lnsum = torch.zeros((L + 1) if save else 2, B * P, 2, **f32) if fused_tm else None
         self.top_a = torch.empty(B, D, **f32)                         # LN(cls / EOT row), projection operand (fp32)
         self.top_stats = torch.empty(2, B, **f32)
         self.rows = torch.empty(B, device=device, dtype=torch.int32)  # cls / EOT row index per sample
@@ -194,6 +203,8 @@ class TowerRT:
 
         if ws.fused_tm:
             self.refresh_w1t(prec)
+            if fused_ln_prologue_enabled():
+                ws.lnsum.zero_()
         for i in range(L):
             self._block_fwd(i, ws, prec, save)
 
@@ -221,13 +232,21 @@ class TowerRT:
         z2 = ws.z2[s] if save else None
         pre = f"{self.blk}.{i}."
         # x + token_mix(LN1(x))                                                          model.py:216,220-222
-        ops.ln_fwd(x, D, self.bp(i, "layerNorm1.weight"), self.bp(i, "layerNorm1.bias"), u, D, st[0], st[1], B * P, D)
+        # Blocks 1..: LayerNorm 1 runs in the PROLOGUE of the fused token-mixing kernel - the preceding lin4 GEMM left the
+        # row sums of x in ws.lnsum (rowstat_out), the kernel normalises the fp32 tile it reads anyway for the residual.
+        fuse_ln = ws.fused_tm and i > 0 and fused_ln_prologue_enabled()
+        if not fuse_ln:
+            ops.ln_fwd(x, D, self.bp(i, "layerNorm1.weight"), self.bp(i, "layerNorm1.bias"), u, D, st[0], st[1], B * P, D)
         w1, ld1 = self.wop(pre + "token_mix_seq.lin1.weight", prec)                       # [4P, P]
         w2, ld2 = self.wop(pre + "token_mix_seq.lin2.weight", prec)                       # [P, 4P]
         if ws.fused_tm:
             # one kernel: both GEMMs, bias, QuickGELU and the residual; the hidden [4P x D] tile never leaves the SM
+            ln = None
+            if fuse_ln:
+                ln = dict(sums=ws.lnsum[i if save else i % 2], gamma=self.bp(i, "layerNorm1.weight"),
+                          beta=self.bp(i, "layerNorm1.bias"), u_out=u, mean=st[0], rstd=st[1])
             ops.token_mix_fwd(B, P, D, u, x, y, w1, ld1, self.bp(i, "token_mix_seq.lin1.bias"), w2, ld2,
-                              self.bp(i, "token_mix_seq.lin2.bias"), w1t=self.w1t[i], ld1t=self.ld1t)
+                              self.bp(i, "token_mix_seq.lin2.bias"), w1t=self.w1t[i], ld1t=self.ld1t, ln=ln)
         else:
             ops.gemm(eng, 4 * P, D, P, B, w1, MAJOR_K, ld1, 0, u, MAJOR_MN, D, P * D, h1, D, 4 * P * D,
                      bias=self.bp(i, "token_mix_seq.lin1.bias"), bias_mode=BIAS_M, zout=z1, ldz=D, z_bs=4 * P * D,
@@ -240,8 +259,13 @@ class TowerRT:
         ops.gemm(eng, B * P, 4 * D, D, 1, v, MAJOR_K, D, 0, w3, MAJOR_K, ld3, 0, h2, 4 * D, 0,
                  bias=self.bp(i, "channel_mix_seq.lin3.bias"), bias_mode=BIAS_N, zout=z2, ldz=4 * D, act=ACT_GELU)
         w4, ld4 = self.wop(pre + "channel_mix_seq.lin4.weight", prec)                     # [D, 4D]
+        nxt = None                                            # row sums of xo for the next block's fused LayerNorm
+        if ws.fused_tm and i + 1 < self.L and fused_ln_prologue_enabled():
+            nxt = ws.lnsum[(i + 1) if save else (i + 1) % 2]
+            if not save:
+                nxt.zero_()                                   # inference: two alternating slots, re-zeroed before every use
         ops.gemm(eng, B * P, D, 4 * D, 1, h2, MAJOR_K, 4 * D, 0, w4, MAJOR_K, ld4, 0, xo, D, 0,
-                 bias=self.bp(i, "channel_mix_seq.lin4.bias"), bias_mode=BIAS_N, R=y, ldr=D)
+                 bias=self.bp(i, "channel_mix_seq.lin4.bias"), bias_mode=BIAS_N, R=y, ldr=D, rowstat_out=nxt)
 
     # ---- backward -------------------------------------------------------------------------------
     def backward(self, ws: TowerWS, du_feat: torch.Tensor, prec: Precision, after_block=None):

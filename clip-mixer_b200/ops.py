@@ -103,7 +103,7 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
          rowsum_out: Optional[torch.Tensor] = None, c_transposed: bool = False,
          A2: Optional[torch.Tensor] = None, a2_major: int = 0, lda2: int = 0, a2_bs: int = 0,
          B2: Optional[torch.Tensor] = None, b2_major: int = 0, ldb2: int = 0, b2_bs: int = 0,
-         bias2: Optional[torch.Tensor] = None):
+         bias2: Optional[torch.Tensor] = None, rowstat_out: Optional[torch.Tensor] = None):
     """acc[m,n] = sum_k A[b][m,k] B[b][n,k] with the fused epilogue of mc_gemm_params.
 
     engine "tc"   -> mc_gemm_bf16_tc  (A, B, zout, zin bf16)
@@ -138,6 +138,9 @@ def gemm(engine: str, M: int, N: int, K: int, batch: int,
     p.A2, p.a2_major, p.lda2, p.a2_batch_stride = _ptr(A2), a2_major, lda2, a2_bs
     p.B2, p.b2_major, p.ldb2, p.b2_batch_stride = _ptr(B2), b2_major, ldb2, b2_bs
     p.bias2 = _ptr(bias2)
+    if rowstat_out is not None and rowstat_out.dtype != torch.float32:
+        raise MixerClipError("gemm: rowstat_out must be fp32")
+    p.rowstat_out = _ptr(rowstat_out)
     fn = lib.mc_gemm_bf16_tc if engine == "tc" else lib.mc_gemm_f32_simt
     if _gemm_timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -175,7 +178,7 @@ def w1_transposed(w1, P, ld1):
 
 def _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t=None, ld1t=0):
     for name, t in (("u", u), ("w1", w1), ("w2", w2)):
-        if t.dtype != torch.bfloat16:
+        if t is not None and t.dtype != torch.bfloat16:
             raise MixerClipError(f"token_mix: operand {name} must be bf16, got {t.dtype}")
     if w1t is None:
         w1t, ld1t = w1_transposed(w1, P, ld1)
@@ -200,10 +203,18 @@ def _tm_call(fn, p, what, B, P, D):
     _count()
 
 
-def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2, w1t=None, ld1t=0):
-    """y = x + W2 g(W1 u + b1) + b2 per sample (model.py:216,220-222), one fused kernel."""
-    p = _tm_params(B, P, D, u, w1, ld1, b1, w2, ld2, w1t, ld1t)
+def token_mix_fwd(B, P, D, u, x, y, w1, ld1, b1, w2, ld2, b2, w1t=None, ld1t=0, ln=None):
+    """y = x + W2 g(W1 u + b1) + b2 per sample (model.py:216,220-222), one fused kernel.
+
+    ln = dict(sums [B*P,2] fp32, gamma [D], beta [D], u_out [B,P,D] bf16, mean [B*P], rstd [B*P]): LayerNorm in the prologue -
+    the kernel computes u = LN(x) itself from the row sums of the producing GEMM (gemm(..., rowstat_out=sums)); `u` is ignored."""
+    p = _tm_params(B, P, D, None if ln is not None else u, w1, ld1, b1, w2, ld2, w1t, ld1t)
     p.b2, p.x, p.y = _ptr(b2), _ptr(x), _ptr(y)
+    if ln is not None:
+        if ln["u_out"].dtype != torch.bfloat16 or any(ln[k].dtype != torch.float32 for k in ("sums", "gamma", "beta", "mean", "rstd")):
+            raise MixerClipError("token_mix_fwd: ln = {sums, gamma, beta, mean, rstd: fp32; u_out: bf16}")
+        p.ln_sums, p.ln_gamma, p.ln_beta = _ptr(ln["sums"]), _ptr(ln["gamma"]), _ptr(ln["beta"])
+        p.u_out, p.ln_mean, p.ln_rstd = _ptr(ln["u_out"]), _ptr(ln["mean"]), _ptr(ln["rstd"])
     _tm_call(_lib.load().mc_token_mix_fwd, p, "token_mix_fwd", B, P, D)
 
 

@@ -115,6 +115,11 @@ typedef struct mc_gemm_params {
     int32_t b2_major;
     int64_t ldb2, b2_batch_stride;
     const float* bias2;
+    /* optional, residual epilogue of the tensor-core engine only (act NONE, fp32 C, R set, batch 1):
+     * rowstat_out[2*m] += sum_n x, rowstat_out[2*m + 1] += sum_n x*x over the values written to C.  Gives the LayerNorm that
+     * follows a channel-mixing lin4 (model.py:216 on the output of :217) its row statistics from the producing GEMM, so
+     * that the fused token-mixing kernel can normalise in its prologue (mc_token_mix_params.ln_sums). */
+    float* rowstat_out;
 } mc_gemm_params;
 
 /* tcgen05 / TMEM / TMA engine: bf16 operands, fp32 accumulation in tensor memory; zout / zin fp16. */
@@ -155,6 +160,17 @@ typedef struct mc_token_mix_params {
     float* gw2;
     int64_t ldg2;
     float* gb1;
+    /* mc_token_mix_fwd only, optional: LayerNorm in the prologue (model.py:216 folded into :220-222).  With ln_sums != NULL
+     * the kernel ignores `u`: it reads the fp32 block input x, normalises it with the per-row (sum, sum of squares) over D
+     * that the producing GEMM left in ln_sums [B*P][2] (mc_gemm_params.rowstat_out) and ln_gamma / ln_beta [D], feeds the
+     * bf16 result to its tensor-core GEMMs and also writes it to u_out [B,P,D] (the backward kernels read it) together
+     * with the row statistics ln_mean / ln_rstd [B*P] (mc_ln_bwd reads them). */
+    const float* ln_sums;
+    const float* ln_gamma;
+    const float* ln_beta;
+    void* u_out;
+    float* ln_mean;
+    float* ln_rstd;
 } mc_token_mix_params;
 int mc_token_mix_supported(int64_t P, int64_t D);
 int mc_token_mix_fwd(const mc_token_mix_params* p, void* stream);

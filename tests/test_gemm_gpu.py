@@ -329,3 +329,24 @@ def test_gemm_tc_streamed_epilogues_on_a_share_of_the_sms(sm_limit):
         run_case("tc", 768, 3072, 50 * 64, a_major=1, b_major=1, accumulate=True, split_k=0)  # dW4
     finally:
         ops.set_sm_limit(0)
+
+
+def test_gemm_tc_residual_epilogue_row_statistics():
+    """mc_gemm_params.rowstat_out: the lin4 epilogue leaves (sum, sum of squares) of every output row for the LayerNorm
+    that the next block's fused token-mixing kernel runs in its prologue."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, N, K = 50 * 24, 768, 512
+    A = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    Bw = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(dev)
+    R = torch.randn(M, N, generator=g).to(dev)
+    C = torch.empty(M, N, device=dev)
+    stat = torch.zeros(M, 2, device=dev)
+    ops.gemm("tc", M, N, K, 1, A, 0, K, 0, Bw, 0, K, 0, C, N, 0, bias=bias, bias_mode=ops.BIAS_N, R=R, ldr=N, rowstat_out=stat)
+    torch.cuda.synchronize()
+    ref = A.double() @ Bw.double().t() + bias.double() + R.double()
+    assert float((C.double() - ref).abs().max()) <= 2e-3
+    assert float((stat[:, 0].double() - C.double().sum(1)).abs().max()) <= 1e-3 * float(C.double().abs().sum(1).max())
+    assert float((stat[:, 1].double() - (C.double() ** 2).sum(1)).abs().max()) <= 1e-5 * float((C.double() ** 2).sum(1).max())

@@ -93,6 +93,39 @@ def test_token_mix_fwd(B, P, D):
 
 
 @pytest.mark.parametrize("B,P,D", SHAPES)
+def test_token_mix_fwd_with_layernorm_in_the_prologue(B, P, D):
+    """model.py:216 folded into :220-222: the kernel normalises the fp32 block input itself from per-row (sum, sum of
+    squares) - what the producing lin4 GEMM leaves in rowstat_out - and also emits u (bf16) and the row statistics."""
+    ops = _ops()
+    t = _setup(B, P, D)
+    dev = t["x"].device
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(B, P, D, generator=g) * 1.7 + 0.4).to(dev)        # non-zero mean: exercises sumsq/D - mean^2
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).to(dev), (torch.randn(D, generator=g) * 0.3).to(dev)
+    xd = x.double()
+    sums = torch.stack([x.sum(-1), (x * x).sum(-1)], dim=-1).reshape(B * P, 2).contiguous()     # fp32, like the GEMM epilogue
+    mean_ref = xd.mean(-1)
+    rstd_ref = 1.0 / torch.sqrt(xd.var(-1, unbiased=False) + 1e-5)
+    u_ref = ((xd - mean_ref[..., None]) * rstd_ref[..., None] * gamma.double() + beta.double())
+    t2 = dict(t)
+    t2["u"], t2["x"] = u_ref.to(torch.bfloat16), x
+    ref = _reference(t2, P)
+    y = torch.full_like(x, float("nan"))
+    u_out = torch.full((B, P, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(B * P, device=dev), torch.empty(B * P, device=dev)
+    ops.token_mix_fwd(B, P, D, None, x, y, t["w1"], t["ld1"], t["b1"], t["w2"], t["ld2"], t["b2"],
+                      ln=dict(sums=sums, gamma=gamma, beta=beta, u_out=u_out, mean=mean, rstd=rstd))
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all() and torch.isfinite(u_out.float()).all()
+    assert _rel(mean, mean_ref.reshape(-1)) <= 1e-5 and _rel(rstd, rstd_ref.reshape(-1)) <= 1e-4
+    assert _rel(u_out, u_ref) <= 4e-3                                   # bf16 rounding of u
+    delta = (y.double() - ref["Y"]).abs().max().item()
+    scale = (ref["Y"] - xd).abs().max().item()
+    assert delta <= 1.2e-2 * scale + 1e-5, (delta, scale)              # u may round to the neighbouring bf16 value
+    assert _rel(y.double() - xd, ref["Y"] - xd) <= 6e-3
+
+
+@pytest.mark.parametrize("B,P,D", SHAPES)
 def test_token_mix_dgrad(B, P, D):
     ops = _ops()
     t = _setup(B, P, D, seed=1)
