@@ -95,7 +95,7 @@ struct TmArgs {
     uint32_t u_tx_bytes;      // bytes one TMA load of a U group delivers (aug: P rows, else Ppad rows)
     uint32_t grp_bytes;       // Ppad * 128: one [Ppad x 64] swizzled group of an activation / weight tile
     uint32_t a_grp_bytes;     // group pitch of the U tile in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
-    uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2;
+    uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2, off_ln;
     const __nv_bfloat16* w1;
     int ld1;
     const __nv_bfloat16* w2;
@@ -187,7 +187,6 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     __shared__ __align__(8) uint64_t y_empty[2];
     __shared__ __align__(8) uint64_t w_full;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float2 lnstat[kMaxTmStages][96];       // (mean, rstd) of the tokens of the tile in each stage (fused LayerNorm)
 
 #ifndef MC_DIVERGENT_WARP_IDX
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index (see gemm_tc.cu)
@@ -201,6 +200,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const uint32_t w1t = base + g.off_w1t, w2t = base + g.off_w2t, hbuf = base + g.off_h, h2buf = base + g.off_h2;
     float* b1s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b1);
     float* b2s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b2);
+    float2* lnstat = reinterpret_cast<float2*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_ln);
     const int SW = g.SW;      // hidden columns per pipeline segment (multiple of 64)
     // WGRAD: CTAs are dealt round-robin to the hidden slices; every slice walks over all tiles
     int slice = 0;
@@ -674,7 +674,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     const float mean = sm.x * invD;
                     const float var = fmaxf(fmaf(-mean, mean, sm.y * invD), 0.f);
                     const float rstd = rsqrtf(var + kLnEps);
-                    lnstat[st_][threadIdx.x] = make_float2(mean, rstd);
+                    lnstat[st_ * 96 + threadIdx.x] = make_float2(mean, rstd);
                     if (d0 == 0) {                                               // one slab per sample writes the saved statistics
                         g.ln_mean[(long long)b * g.P + threadIdx.x] = mean;
                         g.ln_rstd[(long long)b * g.P + threadIdx.x] = rstd;
@@ -691,7 +691,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                     for (int i = 0; i < 16; ++i) {
                         const int p = hsel * 16 + 32 * k + i;
                         if (p < g.P) {
-                            const float2 ms = lnstat[st_][p];
+                            const float2 ms = lnstat[st_ * 96 + p];
                             const __nv_bfloat16 uv = __float2bfloat16_rn(fmaf((xv[k][i] - ms.x) * ms.y, gam, bet));
                             const unsigned short bits = *reinterpret_cast<const unsigned short*>(&uv);
                             asm volatile("st.shared.b16 [%0], %1;" ::"r"(srow + (uint32_t)p * 128u + ((c8 ^ ((uint32_t)p & 7u)) << 4)),
@@ -993,6 +993,8 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     if (mode == TM_WGRAD) off += (uint32_t)natoms_smem * kAtomBytes;
     g.off_b1 = off; off += (uint32_t)g.natoms * 64u * 4u;
     g.off_b2 = off; off += (uint32_t)round_up_i(g.Ppad * 4, 1024);
+    g.off_ln = off;                                // (mean, rstd) of the tile's tokens per stage (fused LayerNorm)
+    if (mode == TM_FWD && p->ln_sums) off += (uint32_t)(kMaxTmStages * 96 * sizeof(float2));
     off = (off + 1023u) & ~1023u;
     g.off_stage = off;
     g.stage_bytes = mode == TM_FWD ? 2u * g.grp_bytes : 2u * g.a_grp_bytes + 2u * g.grp_bytes;
