@@ -44,6 +44,7 @@ namespace {
 
 constexpr int kE1Warps = 16;                                   // four per TMEM lane quarter
 constexpr int kE2Warps = 8;
+constexpr int kLnRows = 10;                                    // token rows per E2 warp in the fused-LayerNorm prologue (P <= 80)
 constexpr int kE1Groups = kE1Warps / 4;
 constexpr int kTmThreads = 128 + 32 * (kE1Warps + kE2Warps);   // 768
 constexpr int kProdWarp = kE1Warps + kE2Warps, kAllocWarp = kProdWarp + 1, kInitWarp = kAllocWarp, kMmaDnWarp = kProdWarp + 2,
@@ -95,7 +96,7 @@ struct TmArgs {
     uint32_t u_tx_bytes;      // bytes one TMA load of a U group delivers (aug: P rows, else Ppad rows)
     uint32_t grp_bytes;       // Ppad * 128: one [Ppad x 64] swizzled group of an activation / weight tile
     uint32_t a_grp_bytes;     // group pitch of the U tile in smem (>= grp_bytes; WGRAD: 16 KB, rows up to 128)
-    uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2, off_ln;
+    uint32_t off_w1t, off_w2t, off_h, off_h2, off_stage, stage_bytes, off_b1, off_b2;
     const __nv_bfloat16* w1;
     int ld1;
     const __nv_bfloat16* w2;
@@ -200,7 +201,6 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const uint32_t w1t = base + g.off_w1t, w2t = base + g.off_w2t, hbuf = base + g.off_h, h2buf = base + g.off_h2;
     float* b1s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b1);
     float* b2s = reinterpret_cast<float*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_b2);
-    float2* lnstat = reinterpret_cast<float2*>(dyn_smem + (base - smem_u32(dyn_smem)) + g.off_ln);
     const int SW = g.SW;      // hidden columns per pipeline segment (multiple of 64)
     // WGRAD: CTAs are dealt round-robin to the hidden slices; every slice walks over all tiles
     int slice = 0;
@@ -657,59 +657,63 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             auto produce = [&](int tp, uint32_t j) {
                 const uint32_t st_ = j % (uint32_t)g.stages, use = j / (uint32_t)g.stages;
                 const int b = tp / g.tiles_d, d0 = (tp - b * g.tiles_d) * 128;
-                const int dl = q * 32 + lane;                                  // channel inside the 128-wide slab
-                const long long gb = ((long long)b * g.P + hsel * 16) * Dd + d0 + dl;
-                if (use > 0) mbar_wait_relaxed(smem_u32(&u_empty[st_]), (use - 1u) & 1u, 32);   // the up GEMMs have read the old tile
-                float xv[3][16];
+                // warp e2 owns tokens e2, e2 + 8, ...; lane = four consecutive channels: a token row of the slab is one
+                // 512-byte line of loads, one 256-byte line of bf16 stores
+                const int c0 = 4 * lane;
+                const long long row0 = (long long)b * g.P + e2;
+                const float* xg = g.x + row0 * Dd + d0 + c0;
+                float4 xv[kLnRows];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int p0 = hsel * 16 + 32 * k;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) xv[k][i] = p0 + i < g.P ? __ldg(g.x + gb + (long long)(32 * k + i) * Dd) : 0.f;
-                }
-                const float gam = __ldg(g.ln_gamma + d0 + dl), bet = __ldg(g.ln_beta + d0 + dl);
-                if ((int)threadIdx.x < g.P) {
-                    const float2 sm = __ldg(reinterpret_cast<const float2*>(g.ln_sums) + (long long)b * g.P + threadIdx.x);
+                for (int k = 0; k < kLnRows; ++k)
+                    if (e2 + 8 * k < g.P) xv[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)(8 * k) * Dd));
+                // lane k holds the statistics of this warp's k-th token
+                float mean_l = 0.f, rstd_l = 0.f;
+                if (lane < kLnRows && e2 + 8 * lane < g.P) {
+                    const float2 sm = __ldg(reinterpret_cast<const float2*>(g.ln_sums) + row0 + 8 * lane);
                     const float invD = 1.0f / (float)Dd;
-                    const float mean = sm.x * invD;
-                    const float var = fmaxf(fmaf(-mean, mean, sm.y * invD), 0.f);
-                    const float rstd = rsqrtf(var + kLnEps);
-                    lnstat[st_ * 96 + threadIdx.x] = make_float2(mean, rstd);
-                    if (d0 == 0) {                                               // one slab per sample writes the saved statistics
-                        g.ln_mean[(long long)b * g.P + threadIdx.x] = mean;
-                        g.ln_rstd[(long long)b * g.P + threadIdx.x] = rstd;
+                    mean_l = sm.x * invD;
+                    rstd_l = rsqrtf(fmaxf(fmaf(-mean_l, mean_l, sm.y * invD), 0.f) + kLnEps);
+                    if (d0 == 0) {                                             // one slab per sample writes the saved statistics
+                        g.ln_mean[row0 + 8 * lane] = mean_l;
+                        g.ln_rstd[row0 + 8 * lane] = rstd_l;
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");                 // the eight E2 warps
-                const uint32_t srow = base + g.off_stage + st_ * g.stage_bytes + (uint32_t)(dl >> 6) * g.a_grp_bytes +
-                                      (uint32_t)(dl & 7) * 2u;
-                const uint32_t c8 = (uint32_t)((dl & 63) >> 3);
-                __nv_bfloat16* ug = g.u_out + gb;
+                const float4 gam = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + d0 + c0));
+                const float4 bet = __ldg(reinterpret_cast<const float4*>(g.ln_beta + d0 + c0));
+                if (use > 0) mbar_wait_relaxed(smem_u32(&u_empty[st_]), (use - 1u) & 1u, 32);   // the up GEMMs have read the old tile
+                const uint32_t sbase = base + g.off_stage + st_ * g.stage_bytes + (uint32_t)(lane >> 4) * g.a_grp_bytes +
+                                       (uint32_t)(lane & 1) * 8u;
+                const uint32_t c8 = (uint32_t)(lane & 15) >> 1;               // 16-byte chunk of the 64-channel group
+                __nv_bfloat16* ug = g.u_out + row0 * Dd + d0 + c0;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = hsel * 16 + 32 * k + i;
-                        if (p < g.P) {
-                            const float2 ms = lnstat[st_ * 96 + p];
-                            const __nv_bfloat16 uv = __float2bfloat16_rn(fmaf((xv[k][i] - ms.x) * ms.y, gam, bet));
-                            const unsigned short bits = *reinterpret_cast<const unsigned short*>(&uv);
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(srow + (uint32_t)p * 128u + ((c8 ^ ((uint32_t)p & 7u)) << 4)),
-                                         "h"(bits) : "memory");
-                            ug[(long long)(32 * k + i) * Dd] = uv;
-                        }
+                for (int k = 0; k < kLnRows; ++k) {
+                    const int p = e2 + 8 * k;
+                    const float mean = __shfl_sync(0xffffffffu, mean_l, k), rstd = __shfl_sync(0xffffffffu, rstd_l, k);
+                    if (p < g.P) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((xv[k].x - mean) * rstd, gam.x, bet.x),
+                                                                        fmaf((xv[k].y - mean) * rstd, gam.y, bet.y));
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((xv[k].z - mean) * rstd, gam.z, bet.z),
+                                                                        fmaf((xv[k].w - mean) * rstd, gam.w, bet.w));
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)p * 128u + ((c8 ^ ((uint32_t)p & 7u)) << 4)),
+                                     "r"(pk.x), "r"(pk.y) : "memory");
+                        *reinterpret_cast<uint2*>(ug + (long long)(8 * k) * Dd) = pk;
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&u_full[st_]));
             };
+            // production runs TWO tiles ahead of the store pass (both stages): the up GEMMs never wait for this warp group
             if (fuse_ln && work0 < g.num_tiles) produce(work0, 0u);
+            if (fuse_ln && work0 + work_stride < g.num_tiles) produce(work0 + work_stride, 1u);
             for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
                 if (fuse_ln) {
-                    if (t + work_stride < g.num_tiles) produce(t + work_stride, n + 1u);   // overlaps the E1 pass of tile t
-                    if (e2 == 0 && lane == 0 && t + 2 * work_stride < g.num_tiles) {        // pull the tile after next into L2
-                        const int t2 = t + 2 * work_stride, b2_ = t2 / g.tiles_d, d2 = (t2 - b2_ * g.tiles_d) * 128;
+                    if (t + 2 * work_stride < g.num_tiles) produce(t + 2 * work_stride, n + 2u);   // its stage: tile t's, read by now
+                    if (e2 == 0 && lane == 0 && t + 3 * work_stride < g.num_tiles) {        // pull the tile after that into L2
+                        const int t2 = t + 3 * work_stride, b2_ = t2 / g.tiles_d, d2 = (t2 - b2_ * g.tiles_d) * 128;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d2 + 32 * i, 0, b2_);
                     }
@@ -861,8 +865,12 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
              (long long)p->P, (long long)p->D);
     const bool fuse_ln_h = mode == TM_FWD && p->ln_sums != nullptr;
     MC_CHECK((p->u || fuse_ln_h) && p->w1 && p->w2 && p->b1, "token_mix: null operand");
-    MC_CHECK(!fuse_ln_h || (p->ln_gamma && p->ln_beta && p->u_out && p->ln_mean && p->ln_rstd && p->P <= 96),
+    MC_CHECK(!fuse_ln_h || (p->ln_gamma && p->ln_beta && p->u_out && p->ln_mean && p->ln_rstd),
              "token_mix fwd with fused LayerNorm: ln_gamma, ln_beta, u_out, ln_mean, ln_rstd are required");
+    MC_CHECK(!fuse_ln_h || (((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->ln_gamma) |
+                              reinterpret_cast<uintptr_t>(p->ln_beta) | reinterpret_cast<uintptr_t>(p->u_out)) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(p->ln_sums) & 7) == 0),
+             "token_mix fwd with fused LayerNorm: x, ln_gamma, ln_beta, u_out must be 16-byte aligned, ln_sums 8-byte aligned");
     MC_CHECK(p->w1t != nullptr && p->ld1t >= 4 * p->P && p->ld1t % 8 == 0 && (reinterpret_cast<uintptr_t>(p->w1t) & 15) == 0,
              "token_mix: w1t (W1^T bf16 [P x ld1t], mc_transpose_bf16 of w1; ld1t >= 4P, multiple of 8, 16-byte aligned) is required");
     TmArgs g{};
@@ -993,8 +1001,6 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     if (mode == TM_WGRAD) off += (uint32_t)natoms_smem * kAtomBytes;
     g.off_b1 = off; off += (uint32_t)g.natoms * 64u * 4u;
     g.off_b2 = off; off += (uint32_t)round_up_i(g.Ppad * 4, 1024);
-    g.off_ln = off;                                // (mean, rstd) of the tile's tokens per stage (fused LayerNorm)
-    if (mode == TM_FWD && p->ln_sums) off += (uint32_t)(kMaxTmStages * 96 * sizeof(float2));
     off = (off + 1023u) & ~1023u;
     g.off_stage = off;
     g.stage_bytes = mode == TM_FWD ? 2u * g.grp_bytes : 2u * g.a_grp_bytes + 2u * g.grp_bytes;
@@ -1008,6 +1014,8 @@ int tm_run(const mc_token_mix_params* p, int mode, cudaStream_t stream) {
     if (g.stages > kMaxTmStages) g.stages = kMaxTmStages;
     // wgrad keeps the activation tile of the previous work item alive while the next one is loaded
     MC_CHECK(mode != TM_WGRAD || g.stages >= 2, "token_mix wgrad: shape does not fit in shared memory");
+    // the fused LayerNorm prologue builds the operand tile two tiles ahead of the store pass
+    MC_CHECK(!fuse_ln_h || g.stages >= 2, "token_mix fwd with fused LayerNorm: shape does not fit in shared memory");
     size_t smem = (size_t)off + (size_t)g.stages * g.stage_bytes + 1024 + slack;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM (each allocates all of TMEM)
     MC_CHECK(smem <= 226 * 1024, "token_mix: shape does not fit in shared memory");
