@@ -164,7 +164,8 @@ typedef struct mc_token_mix_params {
      * the kernel ignores `u`: it reads the fp32 block input x, normalises it with the per-row (sum, sum of squares) over D
      * that the producing GEMM left in ln_sums [B*P][2] (mc_gemm_params.rowstat_out) and ln_gamma / ln_beta [D], feeds the
      * bf16 result to its tensor-core GEMMs and also writes it to u_out [B,P,D] (the backward kernels read it) together
-     * with the row statistics ln_mean / ln_rstd [B*P] (mc_ln_bwd reads them). */
+     * with the row statistics ln_mean / ln_rstd [B*P] (mc_ln_bwd reads them).  x, ln_gamma, ln_beta, u_out: 16-byte
+     * aligned; ln_sums: 8-byte aligned.  Variance = E[x^2] - mean^2 in fp32, clamped at 0, eps 1e-5. */
     const float* ln_sums;
     const float* ln_gamma;
     const float* ln_beta;
