@@ -188,6 +188,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long lo
 // are read from HBM exactly once and the register footprint stays that of a plain row kernel.
 // The fused kernel above keeps serving the gather / class-token variants (3 calls per step).
 // ------------------------------------------------------------------------------------------------
+constexpr int kRowsumLocal = 256;
+
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
@@ -210,6 +212,15 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
         st4(my + c, make_float4(0.f, 0.f, 0.f, 0.f));
         st4(my + W + c, make_float4(0.f, 0.f, 0.f, 0.f));
         st4(my + 2 * W + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    // per-period row sums (the token-mixing lin2 bias gradient: 77 or 50 addresses for ~20 k rows): collected per block in
+    // shared memory, one global atomic per address and block - the 19712 same-address global atomics of the text tower
+    // cost 4 us per launch (profiles/r1s2_rowwise_bench.txt: +rowsum 39.6 us against +colsum 35.6 us)
+    __shared__ float rs_sm[kRowsumLocal];
+    const bool rs_local = rowsum_out != nullptr && rowsum_period <= kRowsumLocal;
+    if (rs_local) {
+        for (int i = threadIdx.x; i < (int)rowsum_period; i += blockDim.x) rs_sm[i] = 0.f;
+        __syncthreads();
     }
     const float invD = 1.0f / D;
     for (long long row = (long long)blockIdx.x * kWarpsPerBlock + warp; row < rows;
@@ -277,11 +288,17 @@ ln_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
         }
         if (rowsum_out != nullptr) {
             rsum = warp_sum(rsum);
-            if (lane == 0) atomicAdd(rowsum_out + row % rowsum_period, rsum);
+            if (lane == 0) {
+                if (rs_local) atomicAdd(&rs_sm[(int)(row % rowsum_period)], rsum);
+                else atomicAdd(rowsum_out + row % rowsum_period, rsum);
+            }
         }
     }
     if (threadIdx.x == 0) pdl_launch_dependents();          // rows done; only the column reductions remain
     __syncthreads();
+    if (rs_local)
+        for (int i = threadIdx.x; i < (int)rowsum_period; i += blockDim.x)
+            if (rs_sm[i] != 0.f) atomicAdd(rowsum_out + i, rs_sm[i]);
     for (int idx = threadIdx.x; idx < 3 * D; idx += blockDim.x) {
         const int which = idx / D, c = idx - which * D;
         float* out = which == 0 ? dgamma : which == 1 ? dbeta : colsum_out;

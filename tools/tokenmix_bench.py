@@ -32,13 +32,28 @@ def run(B, P, D, iters, nbuf, which):
     def fwd(i):
         ops.token_mix_fwd(B, P, D, u[i], x[i], y[i], w1, ld1, b1, w2, ld2, b2, w1t=w1t, ld1t=ld1t)
 
+    # LayerNorm in the prologue: no bf16 operand in, the kernel writes it (u_out) plus mean / rstd
+    sums = torch.stack([x.sum(-1), (x * x).sum(-1)], dim=-1).reshape(nbuf, B * P, 2).contiguous()
+    gam, bet = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev)
+    mean, rstd = torch.empty(B * P, device=dev), torch.empty(B * P, device=dev)
+
+    def fwd_ln(i):
+        ops.token_mix_fwd(B, P, D, None, x[i], y[i], w1, ld1, b1, w2, ld2, b2, w1t=w1t, ld1t=ld1t,
+                          ln=dict(sums=sums[i], gamma=gam, beta=bet, u_out=u[i], mean=mean, rstd=rstd))
+
+    def ln_then_fwd(i):
+        ops.ln_fwd(x[i], D, gam, bet, u[i], D, mean, rstd, B * P, D)
+        fwd(i)
+
     def dgrad(i):
         ops.token_mix_dgrad(B, P, D, u[i], dy[i], y[i], w1, ld1, b1, w2, ld2, w1t=w1t, ld1t=ld1t)
 
     def wgrad(i):
         ops.token_mix_wgrad(B, P, D, u[i], dy[i], w1, ld1, b1, w2, ld2, gw1, ld1, gw2, ld2, gb1, w1t=w1t, ld1t=ld1t)
 
-    for name, fn, bytes_per in (("fwd", fwd, 10), ("dgrad", dgrad, 8), ("wgrad", wgrad, 4)):
+    # fwd_ln / ln+fwd: x fp32 in, u bf16 out, y fp32 out (+ the unfused pair re-reads u and x)
+    for name, fn, bytes_per in (("fwd", fwd, 10), ("fwd_ln", fwd_ln, 10), ("ln+fwd", ln_then_fwd, 10), ("dgrad", dgrad, 8),
+                                ("wgrad", wgrad, 4)):
         if which and name not in which:
             continue
         for i in range(3):
