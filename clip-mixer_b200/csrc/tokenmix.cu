@@ -660,6 +660,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 // warp e2 owns tokens e2, e2 + 8, ...; lane = four consecutive channels: a token row of the slab is one
                 // 512-byte line of loads, one 256-byte line of bf16 stores
                 const int c0 = 4 * lane;
+                TM_TR(warp, 4);
                 const long long row0 = (long long)b * g.P + e2;
                 const float* xg = g.x + row0 * Dd + d0 + c0;
                 float4 xv[kLnRows];
@@ -681,6 +682,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 const float4 gam = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + d0 + c0));
                 const float4 bet = __ldg(reinterpret_cast<const float4*>(g.ln_beta + d0 + c0));
                 if (use > 0) mbar_wait_relaxed(smem_u32(&u_empty[st_]), (use - 1u) & 1u, 32);   // the up GEMMs have read the old tile
+                TM_TR(warp, 5);
                 const uint32_t sbase = base + g.off_stage + st_ * g.stage_bytes + (uint32_t)(lane >> 4) * g.a_grp_bytes +
                                        (uint32_t)(lane & 1) * 8u;
                 const uint32_t c8 = (uint32_t)(lane & 15) >> 1;               // 16-byte chunk of the 64-channel group
@@ -705,6 +707,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&u_full[st_]));
+                TM_TR(warp, 6);
             };
             // production runs TWO tiles ahead of the store pass (both stages): the up GEMMs never wait for this warp group
             if (fuse_ln && work0 < g.num_tiles) produce(work0, 0u);
