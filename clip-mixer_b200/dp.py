@@ -32,21 +32,33 @@ class GradBucketReducer:
     """
 
     def __init__(self, flat_g: torch.Tensor, ranges: List[Tuple[int, int]], group=None, min_bucket_elems: int = 0,
-                 close_after=()):
+                 close_after=(), tail_bucket_elems: int = None):
         self.flat_g, self.group = flat_g, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat_g.is_cuda
         self.comm_stream = torch.cuda.Stream() if self.cuda else None
-        # merge consecutive ranges until each bucket holds at least min_bucket_elems (launch-latency bound)
+        # merge consecutive ranges until each bucket holds at least min_bucket_elems (launch-latency bound).  Towards the
+        # end of a segment (a segment ends at a close_after index: one tower's backward) the threshold drops to
+        # tail_bucket_elems once no more than 1.5 full buckets remain: what is still unreduced when the backward pass ends
+        # is exposed, so the last blocks travel in smaller messages that start earlier.
+        if tail_bucket_elems is None or tail_bucket_elems > min_bucket_elems:
+            tail_bucket_elems = min_bucket_elems
+        remaining, acc = [0] * len(ranges), 0                 # elements from range i to the end of its segment
+        for i in range(len(ranges) - 1, -1, -1):
+            if i in close_after:
+                acc = 0
+            acc += ranges[i][1] - ranges[i][0]
+            remaining[i] = acc
         merged, cur_b, cur_e, members, cur_m = [], None, None, [], []
         for i, (b, e) in enumerate(ranges):
             if cur_b is None:
                 cur_b, cur_e, cur_m = b, e, [i]
+                thr = tail_bucket_elems if 2 * remaining[i] <= 3 * min_bucket_elems else min_bucket_elems
             else:
                 assert b == cur_e, "bucket ranges must be contiguous and in backward order"
                 cur_e = e
                 cur_m.append(i)
-            if cur_e - cur_b >= min_bucket_elems or i in close_after:
+            if cur_e - cur_b >= thr or i in close_after:
                 merged.append((cur_b, cur_e))
                 members.append(cur_m)
                 cur_b = None
@@ -153,6 +165,8 @@ class DataParallel:
             # 8 MB = 27 latency-bound messages, 4.2 ms of all-reduce kernels competing with the persistent GEMMs, 16.31 ms per
             # step; 64-256 MB = 3-7 messages, 1.5-2.2 ms, 15.75-15.84 ms; 64 MB keeps the exposed tail smallest (0.68 ms)
             min_bucket_mb = float(os.environ.get("MC_DP_BUCKET_MB", "64"))
+        # MC_DP_TAIL_MB: bucket size for the last 1.5 buckets' worth of each tower's backward (GradBucketReducer)
+        tail_mb = float(os.environ.get("MC_DP_TAIL_MB", str(min_bucket_mb)))
         self.module, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -162,7 +176,8 @@ class DataParallel:
         # never merge across a tower boundary: autograd may run the two tower backwards in either order
         close = {self.index[("text", "bottom")], self.index[("image", "bottom")]}
         self.reducer = GradBucketReducer(store.flat_g, store.bucket_ranges, group,
-                                         min_bucket_elems=int(min_bucket_mb * (1 << 20) / 4), close_after=close)
+                                         min_bucket_elems=int(min_bucket_mb * (1 << 20) / 4), close_after=close,
+                                         tail_bucket_elems=int(tail_mb * (1 << 20) / 4))
         model._dp = self
 
     def after_block_hook(self, kind: str) -> Optional[Callable]:

@@ -135,6 +135,12 @@ def test_bucket_merging():
     r = GradBucketReducer(g, ranges, None, min_bucket_elems=120, close_after={3})
     assert r.buckets == [(0, 150), (150, 600), (600, 640), (640, 1000)]
     assert r.last_member == {1: 0, 2: 1, 3: 2, 4: 3}
+    # smaller buckets once no more than 1.5 full ones remain in the segment (the exposed end of a tower's backward)
+    ranges = [(i * 50, (i + 1) * 50) for i in range(12)]                      # two segments of six ranges
+    r = GradBucketReducer(torch.zeros(600), ranges, None, min_bucket_elems=100, close_after={5, 11}, tail_bucket_elems=50)
+    assert r.buckets == [(0, 100), (100, 200), (200, 250), (250, 300), (300, 400), (400, 500), (500, 550), (550, 600)]
+    r = GradBucketReducer(torch.zeros(600), ranges, None, min_bucket_elems=100, close_after={5, 11})
+    assert r.buckets == [(0, 100), (100, 200), (200, 300), (300, 400), (400, 500), (500, 600)]
 
 
 # ---- world_size 2 over gloo --------------------------------------------------------------------------
