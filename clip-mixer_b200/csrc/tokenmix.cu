@@ -36,6 +36,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mc {
@@ -712,33 +714,33 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
             // production runs TWO tiles ahead of the store pass (both stages): the up GEMMs never wait for this warp group
             if (fuse_ln && work0 < g.num_tiles) produce(work0, 0u);
             if (fuse_ln && work0 + work_stride < g.num_tiles) produce(work0 + work_stride, 1u);
-            for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
-                if (fuse_ln) {
-                    if (t + 2 * work_stride < g.num_tiles) produce(t + 2 * work_stride, n + 2u);   // its stage: tile t's, read by now
-                    if (e2 == 0 && lane == 0 && t + 3 * work_stride < g.num_tiles) {        // pull the tile after that into L2
-                        const int t2 = t + 3 * work_stride, b2_ = t2 / g.tiles_d, d2 = (t2 - b2_ * g.tiles_d) * 128;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d2 + 32 * i, 0, b2_);
-                    }
-                }
+            // store pass of one tile.  KCH = 16-token chunks per warp (2 up to 64 tokens, else 3), a compile-time constant,
+            // and never more than 32 residual values in flight: with 48 the compiler spilled some right behind their loads,
+            // which put a full global-load latency on this warp's critical path in every tile (-DTM_TRACE timeline,
+            // profiles/r2h_tokenmix_fwd_trace.txt: tag 6 -> 1 in the fused variant, 3 -> 1 in the other)
+            auto store_tile = [&](auto kch_tag, int t) {
+                constexpr int KCH = decltype(kch_tag)::value;
                 const int b = t / g.tiles_d, d0 = (t - b * g.tiles_d) * 128;
                 // this warp owns the 16-token chunks hsel, hsel + 2, hsel + 4: token p = hsel*16 + 32*k + i
                 const long long gbase = ((long long)b * g.P + hsel * 16) * Dd + d0 + q * 32 + lane;
                 const float* xt = g.x + gbase;
                 float* yt = g.y + gbase;
-                float xr[3][16];
-                if (MODE == TM_FWD) {
+                // residual values: two chunks in flight before the accumulator is waited for; a third chunk (65..80 tokens,
+                // warps 0-3 only) reuses the first slot as soon as chunk 0 is stored
+                float xr[2][16];
+                auto load_chunk = [&](int k, float (&dst)[16]) {
+                    const int p0 = hsel * 16 + 32 * k;
+                    if (p0 + 16 <= g.P) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int p0 = hsel * 16 + 32 * k;
-                        if (p0 + 16 <= g.P) {
+                        for (int i = 0; i < 16; ++i) dst[i] = __ldg(xt + (32 * k + i) * Dd);
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) xr[k][i] = __ldg(xt + (32 * k + i) * Dd);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) xr[k][i] = p0 + i < g.P ? __ldg(xt + (32 * k + i) * Dd) : 0.f;
-                        }
+                        for (int i = 0; i < 16; ++i) dst[i] = p0 + i < g.P ? __ldg(xt + (32 * k + i) * Dd) : 0.f;
                     }
+                };
+                if (MODE == TM_FWD) {
+                    load_chunk(0, xr[0]);
+                    load_chunk(1, xr[1]);
                 }
                 const uint32_t yb = ybufs == 2 ? (n & 1u) : 0u;
                 TM_TR(warp, 1);
@@ -746,7 +748,7 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 TM_TR(warp, 2);
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < KCH; ++k) {
                     const int ch = hsel + 2 * k, p0 = hsel * 16 + 32 * k;
                     if (ch < nch) {
                         uint32_t v[16];
@@ -756,11 +758,12 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
                                 const float4 bv = *reinterpret_cast<const float4*>(b2s + p0 + 4 * i4);
-                                o[4 * i4] = xr[k][4 * i4] + bv.x;
-                                o[4 * i4 + 1] = xr[k][4 * i4 + 1] + bv.y;
-                                o[4 * i4 + 2] = xr[k][4 * i4 + 2] + bv.z;
-                                o[4 * i4 + 3] = xr[k][4 * i4 + 3] + bv.w;
+                                o[4 * i4] = xr[k & 1][4 * i4] + bv.x;
+                                o[4 * i4 + 1] = xr[k & 1][4 * i4 + 1] + bv.y;
+                                o[4 * i4 + 2] = xr[k & 1][4 * i4 + 2] + bv.z;
+                                o[4 * i4 + 3] = xr[k & 1][4 * i4 + 3] + bv.w;
                             }
+                            if (k + 2 < KCH && hsel + 2 * (k + 2) < nch) load_chunk(k + 2, xr[k & 1]);
                         } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) o[i] = 0.f;
@@ -780,6 +783,18 @@ token_mix_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
                 __syncwarp();
                 TM_TR(warp, 3);
                 if (lane == 0) mbar_arrive(smem_u32(&y_empty[yb]));
+            };
+            for (int t = work0; t < g.num_tiles; t += work_stride, ++n) {
+                if (fuse_ln) {
+                    if (t + 2 * work_stride < g.num_tiles) produce(t + 2 * work_stride, n + 2u);   // its stage: tile t's, read by now
+                    if (e2 == 0 && lane == 0 && t + 3 * work_stride < g.num_tiles) {        // pull the tile after that into L2
+                        const int t2 = t + 3 * work_stride, b2_ = t2 / g.tiles_d, d2 = (t2 - b2_ * g.tiles_d) * 128;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tm_tma_prefetch_3d(&tmX, d2 + 32 * i, 0, b2_);
+                    }
+                }
+                if (nch <= 4) store_tile(std::integral_constant<int, 2>{}, t);
+                else store_tile(std::integral_constant<int, 3>{}, t);
             }
             if (e2 == 0 && lane == 0) pdl_launch_dependents();   // last tile of this CTA stored
         }
