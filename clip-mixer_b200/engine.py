@@ -24,9 +24,11 @@ from .params import ParamStore
 
 
 def fused_ln_prologue_enabled() -> bool:
-    """MC_TM_FUSE_LN=0 keeps LayerNorm 1 of every block as its own kernel (A/B); default: blocks 1.. take it in the
-    prologue of the fused token-mixing forward kernel, with row statistics from the preceding lin4 GEMM's epilogue."""
-    return os.environ.get("MC_TM_FUSE_LN", "1") != "0"
+    """MC_TM_FUSE_LN=1: LayerNorm 1 of blocks 1.. runs in the prologue of the fused token-mixing forward kernel, with row
+    statistics from the preceding lin4 GEMM's epilogue, instead of as its own kernel.  Off by default: parity-green and
+    22 launches fewer, but the store warps that do the normalising are the forward kernel's bottleneck - interleaved A/B
+    14.46 / 14.92 ms without against 15.17 / 14.84 ms with (profiles/r2i_fuse_ln_ab.txt)."""
+    return os.environ.get("MC_TM_FUSE_LN", "0") == "1"
 
 
 def fused_token_mix_enabled() -> bool:

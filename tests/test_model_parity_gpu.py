@@ -212,6 +212,35 @@ def test_b32_full_size_vs_oracle(precision):
     check(out, truth, TOL[precision], f"B32/{precision}")
 
 
+def test_b32_full_size_vs_oracle_with_layernorm_in_the_token_mixing_prologue(monkeypatch):
+    """The same check with MC_TM_FUSE_LN=1: LayerNorm 1 of blocks 1.. (model.py:216) runs inside the fused token-mixing
+    forward kernel from the row sums the preceding lin4 GEMM leaves (opt-in schedule, engine.fused_ln_prologue_enabled)."""
+    from oracle import mixer_clip_oracle as O
+    from clip_mixer_b200 import engine
+    monkeypatch.setenv("MC_TM_FUSE_LN", "1")
+    assert engine.fused_ln_prologue_enabled()
+    cfg = O.CONFIGS["B32"]
+    sd = O.seeded_state_dict(cfg, seed=0)
+    image, text = O.synthetic_batch(cfg, 16, seed=1)
+    torch.set_num_threads(os.cpu_count())
+    truth = O.loss_and_grads({k: v.double() for k, v in sd.items()}, image.double(), text)
+    model = _build(cfg, sd, "bf16")
+    launches0 = _launch_count()
+    out = reference_style_step(model, image.to(DEV), text.to(DEV))
+    fused_launches = _launch_count() - launches0
+    check(out, truth, TOL["bf16"], "B32/bf16/ln-prologue")
+    monkeypatch.setenv("MC_TM_FUSE_LN", "0")
+    model.zero_grad(set_to_none=True)
+    launches0 = _launch_count()
+    reference_style_step(model, image.to(DEV), text.to(DEV))
+    assert _launch_count() - launches0 == fused_launches + 22          # one mc_ln_fwd per block and tower except block 0
+
+
+def _launch_count():
+    from clip_mixer_b200 import ops
+    return ops.launch_count()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_b16_token_mixing_heavy_shape_vs_oracle(precision):
     """BASELINE.json configs[3] architecture (patch 16 -> 197 image tokens, token-mix 197 -> 788 -> 197), 2+2 layers,
