@@ -26,10 +26,9 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.mc_version() >= 100
 
 
-def test_gemm_params_struct_matches_header_field_order():
-    from clip_mixer_b200._lib import GemmParams
+def _header_struct_fields(tag):
     header = open(os.path.join(ROOT, "include", "mixerclip.h")).read()
-    body = header[header.index("typedef struct mc_gemm_params {"):header.index("} mc_gemm_params;")]
+    body = header[header.index("typedef struct %s {" % tag):header.index("} %s;" % tag)]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split("{", 1)[1].split(";"):
@@ -40,7 +39,18 @@ def test_gemm_params_struct_matches_header_field_order():
         first = parts[0].split()[-1]
         names.append(first)
         names += [p.strip() for p in parts[1:]]
-    assert names == [f[0] for f in GemmParams._fields_]
+    return names
+
+
+def test_gemm_params_struct_matches_header_field_order():
+    from clip_mixer_b200._lib import GemmParams
+    assert _header_struct_fields("mc_gemm_params") == [f[0] for f in GemmParams._fields_]
+
+
+def test_token_mix_params_struct_matches_header_field_order():
+    """The ctypes mirror of mc_token_mix_params (incl. the LayerNorm-prologue fields at its end) follows the header."""
+    from clip_mixer_b200._lib import TokenMixParams
+    assert _header_struct_fields("mc_token_mix_params") == [f[0] for f in TokenMixParams._fields_]
 
 
 def test_no_cpu_fallback():
